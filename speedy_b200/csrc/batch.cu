@@ -1,0 +1,775 @@
+// Batch context: device-resident state of N independent streams and the C-ABI
+// entry points of include/speedy_b200.h (section 2).  Host logic only, plus the
+// three bookkeeping kernels (input-tail carry, output read, synthetic input).
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/speedy_b200.h"
+#include "kernels.cuh"
+#include "synth.h"
+
+namespace speedy {
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+static thread_local std::string g_error;
+static void set_error(const std::string& e) { g_error = e; }
+
+#define CU_TRY(expr)                                                              \
+  do {                                                                            \
+    cudaError_t _e = (expr);                                                      \
+    if (_e != cudaSuccess) {                                                      \
+      set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));              \
+      return 0;                                                                   \
+    }                                                                             \
+  } while (0)
+
+// ---------------------------------------------------------------------------
+// bookkeeping kernels
+// ---------------------------------------------------------------------------
+
+// After a write: keep the last hist_frames sample frames of every stream (the
+// delayed audio Sonic has not consumed yet plus the analysis overlap), advance
+// the stream total.  soniclib.c keeps the same data in its ring of 10 ms buffers
+// (soniclib.c:186-233) and upstream Sonic in its input FIFO.
+__global__ void __launch_bounds__(128) tail_kernel(TailParams p) {
+  const int s = blockIdx.x;
+  const Geometry& g = p.g;
+  const long long t_old = p.st.total[s];
+  const long long t_new = t_old + (p.counts ? p.counts[s] : p.frames);
+  const long long old_base = p.st.hist_base[s];
+  long long nb = t_new - g.hist_frames;
+  if (nb < old_base) nb = old_base;
+  Source src;
+  src.channels = g.channels;
+  src.hist = p.hist_src + (size_t)s * p.hist_stride;
+  src.in = p.in ? p.in + (size_t)s * p.in_stride_frames * g.channels : nullptr;
+  src.hist_base = old_base;
+  src.t_old = t_old;
+  src.t_new = t_new;
+  int16_t* dst = p.hist_dst + (size_t)s * p.hist_stride;
+  const long long total = (t_new - nb) * g.channels;
+  const long long first = nb * g.channels;
+  for (long long i = threadIdx.x; i < total; i += blockDim.x) {
+    long long e = first + i;
+    long long frame = e / g.channels;
+    dst[i] = (int16_t)src.raw(frame, (int)(e - frame * g.channels));
+  }
+  __syncthreads();  // all reads of total/hist_base above are done
+  if (threadIdx.x == 0) {
+    if (p.st.sonic_head[s] < nb) atomicOr(&p.st.status[s], SPEEDY_STATUS_INPUT_OVERFLOW);
+    p.st.total[s] = t_new;
+    p.st.hist_base[s] = nb;
+  }
+}
+
+cudaError_t launch_tail(const TailParams& p, cudaStream_t stream) {
+  tail_kernel<<<p.n_streams, 128, 0, stream>>>(p);
+  count_launch();
+  return cudaGetLastError();
+}
+
+// sonicReadShortFromStream for every stream: copy the pending output.
+__global__ void __launch_bounds__(256) read_copy_kernel(const int16_t* out, long long cap, int channels,
+                                                        const int* pending, int16_t* dst,
+                                                        long long dst_stride) {
+  const int s = blockIdx.y;
+  long long n = pending[s];
+  if (n > dst_stride) n = dst_stride;
+  const long long total = n * channels;
+  const int16_t* src = out + (size_t)s * cap * channels;
+  int16_t* d = dst + (size_t)s * dst_stride * channels;
+  // 16-byte vectors when both rows are aligned
+  const bool aligned = ((((size_t)src) | ((size_t)d)) & 15) == 0;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (aligned) {
+    const long long nv = total / 8;
+    const int4* sv = reinterpret_cast<const int4*>(src);
+    int4* dv = reinterpret_cast<int4*>(d);
+    for (long long i = tid; i < nv; i += stride) dv[i] = sv[i];
+    for (long long i = nv * 8 + tid; i < total; i += stride) d[i] = src[i];
+  } else {
+    for (long long i = tid; i < total; i += stride) d[i] = src[i];
+  }
+}
+
+__global__ void read_finish_kernel(int n, int* pending, int* status, int* counts, long long dst_stride) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  int c = pending[s];
+  if (counts) {
+    if (c > dst_stride) {
+      atomicOr(&status[s], SPEEDY_STATUS_READ_TRUNCATED);
+      c = (int)dst_stride;
+    }
+    counts[s] = c;
+  }
+  pending[s] = 0;
+}
+
+__global__ void __launch_bounds__(256) synth_kernel(int16_t* out, unsigned long long first_id, int rate,
+                                                    int channels, long long frames) {
+  const int s = blockIdx.y;
+  int16_t* row = out + (size_t)s * frames * channels;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < frames; n += stride) {
+    int32_t x = synth_mono(first_id + s, rate, n);
+    for (int c = 0; c < channels; c++) {
+      int32_t v = x;
+      if (channels > 1) v = (c & 1) ? (x * 11) / 10 : (x * 9) / 10;
+      if (v > 32767) v = 32767;
+      if (v < -32768) v = -32768;
+      row[n * channels + c] = (int16_t)v;
+    }
+  }
+}
+
+__global__ void fill_float_kernel(float* p, long long n, float v) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// ---------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------
+static void make_geometry(int rate, int channels, int match_matlab, Geometry* g) {
+  g->rate = rate;
+  g->channels = channels;
+  g->window = (int)(1.5 * rate / (float)100.0);  // speedy.c:213
+  g->fft = 2 * g->window;                        // speedy.c:214
+  g->step = (int)(rate / 100.0);                 // speedy.c:335-338
+  g->partial = g->window - (g->window / g->step) * g->step;  // soniclib.c:410-411
+  g->future = match_matlab ? 8 : 12;             // speedy.h:136-146
+  g->past = match_matlab ? 12 : 8;
+  g->min_period = rate / 400;                    // SONIC_MAX_PITCH
+  g->max_period = rate / 65;                     // SONIC_MIN_PITCH
+  g->max_required = 2 * g->max_period;
+  g->skip = rate > 4000 ? rate / 4000 : 1;       // SONIC_AMDF_FREQ
+  g->hist_frames = g->max_required + (g->future + 4) * g->step + g->window + 64;
+}
+
+static int factorize(int n, int* f) {
+  int c = 0;
+  while (n % 4 == 0) { f[c++] = 4; n /= 4; }
+  while (n % 2 == 0) { f[c++] = 2; n /= 2; }
+  for (int p = 3; n > 1; p += 2) {
+    while (n % p == 0) {
+      if (c >= kMaxFactors) return -1;
+      f[c++] = p;
+      n /= p;
+    }
+  }
+  return c;
+}
+
+}  // namespace speedy
+
+using namespace speedy;
+
+struct speedyBatchStruct {
+  speedyBatchConfig cfg;
+  Geometry g;
+  int n;
+  cudaStream_t own_stream;
+  StreamState st;
+  std::vector<void*> allocs;
+  // tables
+  float* d_window;
+  float2* d_tw_n;
+  float2* d_tw_half;
+  int n_factors;
+  int factors[kMaxFactors];
+  // history (ping-pong)
+  int16_t* d_hist[2];
+  int hist_cur;
+  long long hist_stride;
+  // scratch
+  int max_new_frames;
+  float2* d_feat;
+  float* d_speeds;
+  int speeds_stride;
+  // output
+  int16_t* d_out;
+  long long out_capacity;
+  // override speeds
+  float* d_override;
+  long long override_stride;
+  // taps
+  float *d_tap_spec, *d_tap_energy, *d_tap_features, *d_tap_tension, *d_tap_speed;
+  long long last_frames;           // the last write, for GetTaps
+  const int32_t* last_d_counts;
+  // host staging for the host-pointer entry points
+  int16_t* d_stage;
+  long long stage_frames;
+  int32_t* d_counts_stage;
+  int32_t* h_pinned_counts;
+  // child contexts used by speedyBatchProcess
+  std::vector<speedyBatch> slabs;
+  int16_t* d_slab_in;
+};
+
+namespace {
+
+template <typename T>
+bool dev_alloc(speedyBatch b, T** p, size_t count) {
+  void* q = nullptr;
+  cudaError_t e = cudaMalloc(&q, count * sizeof(T) > 0 ? count * sizeof(T) : 16);
+  if (e != cudaSuccess) {
+    set_error(std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    return false;
+  }
+  b->allocs.push_back(q);
+  *p = reinterpret_cast<T*>(q);
+  return true;
+}
+
+cudaStream_t pick_stream(speedyBatch b, void* s) { return s ? (cudaStream_t)s : b->own_stream; }
+
+int fill_floats(speedyBatch b, float* d, const float* values, float uniform, cudaStream_t st) {
+  if (values) {
+    CU_TRY(cudaMemcpyAsync(d, values, sizeof(float) * b->n, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaStreamSynchronize(st));
+  } else {
+    fill_float_kernel<<<(b->n + 255) / 256, 256, 0, st>>>(d, b->n, uniform);
+    CU_TRY(cudaGetLastError());
+  }
+  return 1;
+}
+
+int reset_state(speedyBatch b, cudaStream_t st) {
+  const int n = b->n;
+  StreamState& s = b->st;
+  CU_TRY(cudaMemsetAsync(s.total, 0, sizeof(long long) * n, st));
+  CU_TRY(cudaMemsetAsync(s.status, 0, sizeof(int) * n, st));
+  // speedy.c:287-292: both one-pole filters start at the long-term means
+  fill_float_kernel<<<(n + 255) / 256, 256, 0, st>>>(s.lp_energy, n, 2.14204f);
+  fill_float_kernel<<<(n + 255) / 256, 256, 0, st>>>(s.lp_diff, n, 123.837f);
+  CU_TRY(cudaMemsetAsync(s.cur_dur, 0, sizeof(float) * n, st));
+  CU_TRY(cudaMemsetAsync(s.des_dur, 0, sizeof(float) * n, st));
+  CU_TRY(cudaMemsetAsync(s.ring_comp, 0, sizeof(float) * n * kRing, st));
+  CU_TRY(cudaMemsetAsync(s.ring_energy, 0, sizeof(float) * n * kRing, st));
+  CU_TRY(cudaMemsetAsync(s.ring_lsd, 0, sizeof(float) * n * kRing, st));
+  CU_TRY(cudaMemsetAsync(s.sonic_head, 0, sizeof(long long) * n, st));
+  CU_TRY(cudaMemsetAsync(s.sonic_fed, 0, sizeof(long long) * n, st));
+  CU_TRY(cudaMemsetAsync(s.prev_period, 0, sizeof(int) * n, st));
+  CU_TRY(cudaMemsetAsync(s.prev_min_diff, 0, sizeof(int) * n, st));
+  CU_TRY(cudaMemsetAsync(s.remaining_copy, 0, sizeof(int) * n, st));
+  CU_TRY(cudaMemsetAsync(s.out_total, 0, sizeof(long long) * n, st));
+  CU_TRY(cudaMemsetAsync(s.out_count, 0, sizeof(int) * n, st));
+  CU_TRY(cudaMemsetAsync(s.hist_base, 0, sizeof(long long) * n, st));
+  CU_TRY(cudaGetLastError());
+  b->hist_cur = 0;
+  return 1;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* speedyBatchLastError(void) { return g_error.c_str(); }
+
+int64_t speedyBatchKernelLaunches(void) { return g_launches.load(); }
+
+const char* speedyBatchBuildInfo(void) {
+  return "speedy_b200 sm_100a: k1_spectral_480<4 warps> (radix-8 x radix-15 real FFT) | "
+         "k1_spectral_generic<128> | k2_tension | k4_sonic<32|64|128> | tail | read | synth";
+}
+
+void speedyBatchDefaultConfig(speedyBatchConfig* cfg) {
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->sample_rate = 16000;
+  cfg->num_channels = 1;
+  cfg->num_streams = 1;
+  cfg->match_matlab = 0;
+  cfg->speed = 1.0f;              // soniclib.c:114
+  cfg->nonlinear_factor = 0.0f;   // soniclib.c:117
+  cfg->feedback_strength = 0.1f;  // soniclib.c:122
+  cfg->device = 0;
+  cfg->max_write_frames = 16000;
+  cfg->out_capacity = 0;
+  cfg->taps = 0;
+  cfg->threads_per_stream = 0;
+}
+
+int speedyBatchFrameGeometry(int sample_rate, int* window, int* fft, int* step) {
+  if (sample_rate < 800) return 0;
+  Geometry g;
+  make_geometry(sample_rate, 1, 0, &g);
+  if (window) *window = g.window;
+  if (fft) *fft = g.fft;
+  if (step) *step = g.step;
+  return 1;
+}
+
+int speedyBatchNumStreams(speedyBatch b) { return b ? b->n : 0; }
+
+void speedyBatchDestroy(speedyBatch b) {
+  if (!b) return;
+  cudaSetDevice(b->cfg.device);
+  for (speedyBatch c : b->slabs) speedyBatchDestroy(c);
+  for (void* p : b->allocs) cudaFree(p);
+  if (b->h_pinned_counts) cudaFreeHost(b->h_pinned_counts);
+  if (b->own_stream) cudaStreamDestroy(b->own_stream);
+  delete b;
+}
+
+speedyBatch speedyBatchCreate(const speedyBatchConfig* cfg) {
+  if (!cfg || cfg->num_streams < 1 || cfg->num_channels < 1 || cfg->sample_rate < 800 ||
+      cfg->max_write_frames < 1) {
+    set_error("speedyBatchCreate: bad configuration");
+    return nullptr;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || cfg->device >= ndev) {
+    set_error("speedyBatchCreate: no CUDA device (this library has no CPU fallback)");
+    return nullptr;
+  }
+  if (cudaSetDevice(cfg->device) != cudaSuccess) {
+    set_error("speedyBatchCreate: cudaSetDevice failed");
+    return nullptr;
+  }
+  speedyBatch b = new speedyBatchStruct();
+  b->cfg = *cfg;
+  b->n = cfg->num_streams;
+  b->own_stream = nullptr;
+  b->h_pinned_counts = nullptr;
+  b->d_stage = nullptr;
+  b->stage_frames = 0;
+  b->d_counts_stage = nullptr;
+  b->d_override = nullptr;
+  b->override_stride = 0;
+  b->d_slab_in = nullptr;
+  b->d_tap_spec = b->d_tap_energy = b->d_tap_features = b->d_tap_tension = b->d_tap_speed = nullptr;
+  make_geometry(cfg->sample_rate, cfg->num_channels, cfg->match_matlab, &b->g);
+  const Geometry& g = b->g;
+  b->n_factors = factorize(g.fft, b->factors);
+  bool ok = b->n_factors > 0;
+  if (!ok) set_error("speedyBatchCreate: unsupported FFT size");
+  for (int i = 0; ok && i < b->n_factors; i++) {
+    if (b->factors[i] > 61) {
+      ok = false;
+      set_error("speedyBatchCreate: FFT size has a large prime factor");
+    }
+  }
+  if (ok && cudaStreamCreateWithFlags(&b->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    ok = false;
+    set_error("speedyBatchCreate: cudaStreamCreate failed");
+  }
+  const int n = b->n;
+  StreamState& s = b->st;
+  ok = ok && dev_alloc(b, &s.total, n) && dev_alloc(b, &s.status, n) && dev_alloc(b, &s.speed, n) &&
+       dev_alloc(b, &s.nonlinear, n) && dev_alloc(b, &s.feedback, n) && dev_alloc(b, &s.lp_energy, n) &&
+       dev_alloc(b, &s.lp_diff, n) && dev_alloc(b, &s.cur_dur, n) && dev_alloc(b, &s.des_dur, n) &&
+       dev_alloc(b, &s.ring_comp, (size_t)n * kRing) && dev_alloc(b, &s.ring_energy, (size_t)n * kRing) &&
+       dev_alloc(b, &s.ring_lsd, (size_t)n * kRing) && dev_alloc(b, &s.ring_lp, 1) &&
+       dev_alloc(b, &s.sonic_head, n) && dev_alloc(b, &s.sonic_fed, n) && dev_alloc(b, &s.prev_period, n) &&
+       dev_alloc(b, &s.prev_min_diff, n) && dev_alloc(b, &s.remaining_copy, n) &&
+       dev_alloc(b, &s.sonic_speed, n) && dev_alloc(b, &s.out_total, n) && dev_alloc(b, &s.out_count, n) &&
+       dev_alloc(b, &s.hist_base, n);
+  // tables (speedy.c:256-258 Hamming in double, stored float; FFT roots likewise)
+  if (ok) {
+    std::vector<float> w(g.window);
+    for (int i = 0; i < g.window; i++) w[i] = (float)(0.54 - 0.46 * cos(2 * M_PI * i / (g.window - 1.0)));
+    std::vector<float2> tn(g.fft), th(g.fft / 2);
+    for (int k = 0; k < g.fft; k++) {
+      double ph = -2.0 * M_PI * k / g.fft;
+      tn[k] = make_float2((float)cos(ph), (float)sin(ph));
+    }
+    for (int k = 0; k < g.fft / 2; k++) {
+      double ph = -2.0 * M_PI * k / (g.fft / 2);
+      th[k] = make_float2((float)cos(ph), (float)sin(ph));
+    }
+    ok = dev_alloc(b, &b->d_window, g.window) && dev_alloc(b, &b->d_tw_n, g.fft) &&
+         dev_alloc(b, &b->d_tw_half, g.fft / 2);
+    if (ok) {
+      cudaMemcpy(b->d_window, w.data(), sizeof(float) * g.window, cudaMemcpyHostToDevice);
+      cudaMemcpy(b->d_tw_n, tn.data(), sizeof(float2) * g.fft, cudaMemcpyHostToDevice);
+      cudaMemcpy(b->d_tw_half, th.data(), sizeof(float2) * (g.fft / 2), cudaMemcpyHostToDevice);
+    }
+  }
+  // history, scratch, output
+  b->hist_stride = (long long)g.hist_frames * g.channels;
+  b->max_new_frames = (int)(cfg->max_write_frames / g.step) + 2;
+  b->speeds_stride = b->max_new_frames;
+  b->out_capacity = cfg->out_capacity > 0 ? cfg->out_capacity
+                                          : cfg->max_write_frames + 4 * (long long)g.max_required;
+  ok = ok && dev_alloc(b, &b->d_hist[0], (size_t)n * b->hist_stride) &&
+       dev_alloc(b, &b->d_hist[1], (size_t)n * b->hist_stride) &&
+       dev_alloc(b, &b->d_feat, (size_t)n * b->max_new_frames) &&
+       dev_alloc(b, &b->d_speeds, (size_t)n * b->speeds_stride) &&
+       dev_alloc(b, &b->d_out, (size_t)n * b->out_capacity * g.channels) &&
+       dev_alloc(b, &b->d_counts_stage, n);
+  const size_t tap_rows = (size_t)n * b->max_new_frames;
+  if (ok && (cfg->taps & SPEEDY_TAP_SPECTROGRAM)) ok = dev_alloc(b, &b->d_tap_spec, tap_rows * g.fft);
+  if (ok && (cfg->taps & SPEEDY_TAP_ENERGY)) ok = dev_alloc(b, &b->d_tap_energy, tap_rows);
+  if (ok && (cfg->taps & SPEEDY_TAP_FEATURES)) ok = dev_alloc(b, &b->d_tap_features, tap_rows * kFeatureCount);
+  if (ok && (cfg->taps & SPEEDY_TAP_TENSION)) ok = dev_alloc(b, &b->d_tap_tension, tap_rows);
+  if (ok && (cfg->taps & SPEEDY_TAP_SPEED)) ok = dev_alloc(b, &b->d_tap_speed, tap_rows);
+  if (ok && cudaMallocHost((void**)&b->h_pinned_counts, sizeof(int32_t) * n) != cudaSuccess) {
+    ok = false;
+    set_error("speedyBatchCreate: cudaMallocHost failed");
+  }
+  if (ok) {
+    ok = reset_state(b, b->own_stream) && fill_floats(b, s.speed, nullptr, cfg->speed, b->own_stream) &&
+         fill_floats(b, s.sonic_speed, nullptr, cfg->speed, b->own_stream) &&
+         fill_floats(b, s.nonlinear, nullptr, cfg->nonlinear_factor, b->own_stream) &&
+         fill_floats(b, s.feedback, nullptr, cfg->feedback_strength, b->own_stream);
+    if (ok && cudaStreamSynchronize(b->own_stream) != cudaSuccess) {
+      ok = false;
+      set_error("speedyBatchCreate: initialisation kernels failed");
+    }
+  }
+  b->last_frames = 0;
+  b->last_d_counts = nullptr;
+  if (!ok) {
+    speedyBatchDestroy(b);
+    return nullptr;
+  }
+  return b;
+}
+
+int speedyBatchReset(speedyBatch b, void* cuda_stream) {
+  if (!b) return 0;
+  cudaStream_t st = pick_stream(b, cuda_stream);
+  CU_TRY(cudaSetDevice(b->cfg.device));
+  if (!reset_state(b, st)) return 0;
+  // sonicSetSpeed also hands the speed to Sonic (soniclib.c:181-182)
+  CU_TRY(cudaMemcpyAsync(b->st.sonic_speed, b->st.speed, sizeof(float) * b->n, cudaMemcpyDeviceToDevice, st));
+  b->last_frames = 0;
+  b->last_d_counts = nullptr;
+  return 1;
+}
+
+int speedyBatchSetSpeed(speedyBatch b, const float* values, float uniform) {
+  if (!b) return 0;
+  CU_TRY(cudaSetDevice(b->cfg.device));
+  // soniclib.c:177-183: remembered as R_g and handed to Sonic at once
+  return fill_floats(b, b->st.speed, values, uniform, b->own_stream) &&
+         fill_floats(b, b->st.sonic_speed, values, uniform, b->own_stream) &&
+         cudaStreamSynchronize(b->own_stream) == cudaSuccess;
+}
+
+int speedyBatchSetNonlinear(speedyBatch b, const float* values, float uniform) {
+  if (!b) return 0;
+  CU_TRY(cudaSetDevice(b->cfg.device));
+  return fill_floats(b, b->st.nonlinear, values, uniform, b->own_stream) &&
+         cudaStreamSynchronize(b->own_stream) == cudaSuccess;
+}
+
+int speedyBatchSetFeedback(speedyBatch b, const float* values, float uniform) {
+  if (!b) return 0;
+  CU_TRY(cudaSetDevice(b->cfg.device));
+  return fill_floats(b, b->st.feedback, values, uniform, b->own_stream) &&
+         cudaStreamSynchronize(b->own_stream) == cudaSuccess;
+}
+
+int speedyBatchOverrideSpeeds(speedyBatch b, const float* speeds, int64_t frames_per_stream) {
+  if (!b) return 0;
+  CU_TRY(cudaSetDevice(b->cfg.device));
+  if (!speeds) {
+    b->d_override = nullptr;
+    b->override_stride = 0;
+    return 1;
+  }
+  float* d = nullptr;
+  if (!dev_alloc(b, &d, (size_t)b->n * frames_per_stream)) return 0;
+  CU_TRY(cudaMemcpy(d, speeds, sizeof(float) * b->n * frames_per_stream, cudaMemcpyHostToDevice));
+  b->d_override = d;
+  b->override_stride = frames_per_stream;
+  return 1;
+}
+
+int speedyBatchWriteDevice(speedyBatch b, const int16_t* d_in, int64_t stride_frames, int64_t frames,
+                           const int32_t* d_counts, void* cuda_stream) {
+  if (!b) return 0;
+  if (frames < 0 || frames > b->cfg.max_write_frames) {
+    set_error("speedyBatchWriteDevice: frames exceeds max_write_frames");
+    return 0;
+  }
+  if (frames == 0) return 1;
+  CU_TRY(cudaSetDevice(b->cfg.device));
+  cudaStream_t st = pick_stream(b, cuda_stream);
+  const Geometry& g = b->g;
+
+  K1Params k1;
+  memset(&k1, 0, sizeof(k1));
+  k1.g = g;
+  k1.st = b->st;
+  k1.n_streams = b->n;
+  k1.hist = b->d_hist[b->hist_cur];
+  k1.hist_stride = b->hist_stride;
+  k1.in = d_in;
+  k1.in_stride_frames = stride_frames;
+  k1.counts = d_counts;
+  k1.frames = frames;
+  k1.feat = b->d_feat;
+  // at most this many analysis windows can complete in one write
+  k1.max_new_frames = (int)(frames / g.step) + 2;
+  if (k1.max_new_frames > b->max_new_frames) k1.max_new_frames = b->max_new_frames;
+  k1.window = b->d_window;
+  k1.tw_n = b->d_tw_n;
+  k1.tw_half = b->d_tw_half;
+  k1.n_factors = b->n_factors;
+  memcpy(k1.factors, b->factors, sizeof(k1.factors));
+  k1.tap_spec = b->d_tap_spec;
+  k1.tap_stride = b->max_new_frames;
+  CU_TRY(launch_k1(k1, st));  // streams with nonlinear factor 0 skip themselves
+
+  K2Params k2;
+  memset(&k2, 0, sizeof(k2));
+  k2.g = g;
+  k2.st = b->st;
+  k2.n_streams = b->n;
+  k2.counts = d_counts;
+  k2.frames = frames;
+  k2.feat = b->d_feat;
+  k2.max_new_frames = b->max_new_frames;
+  k2.speeds = b->d_speeds;
+  k2.speeds_stride = b->speeds_stride;
+  k2.override_speeds = b->d_override;
+  k2.override_stride = b->override_stride;
+  k2.tap_features = b->d_tap_features;
+  k2.tap_tension = b->d_tap_tension;
+  k2.tap_speed = b->d_tap_speed;
+  k2.tap_energy = b->d_tap_energy;
+  CU_TRY(launch_k2(k2, st));
+
+  K4Params k4;
+  memset(&k4, 0, sizeof(k4));
+  k4.g = g;
+  k4.st = b->st;
+  k4.n_streams = b->n;
+  k4.hist = b->d_hist[b->hist_cur];
+  k4.hist_stride = b->hist_stride;
+  k4.in = d_in;
+  k4.in_stride_frames = stride_frames;
+  k4.counts = d_counts;
+  k4.frames = frames;
+  k4.speeds = b->d_speeds;
+  k4.speeds_stride = b->speeds_stride;
+  k4.flush = 0;
+  k4.out = b->d_out;
+  k4.out_capacity = b->out_capacity;
+  k4.threads_per_stream = b->cfg.threads_per_stream;
+  CU_TRY(launch_k4(k4, st));
+
+  TailParams tp;
+  memset(&tp, 0, sizeof(tp));
+  tp.g = g;
+  tp.st = b->st;
+  tp.n_streams = b->n;
+  tp.hist_src = b->d_hist[b->hist_cur];
+  tp.hist_dst = b->d_hist[b->hist_cur ^ 1];
+  tp.hist_stride = b->hist_stride;
+  tp.in = d_in;
+  tp.in_stride_frames = stride_frames;
+  tp.counts = d_counts;
+  tp.frames = frames;
+  CU_TRY(launch_tail(tp, st));
+  b->hist_cur ^= 1;
+  b->last_frames = frames;
+  b->last_d_counts = d_counts;
+  return 1;
+}
+
+int speedyBatchFlushDevice(speedyBatch b, void* cuda_stream) {
+  if (!b) return 0;
+  CU_TRY(cudaSetDevice(b->cfg.device));
+  cudaStream_t st = pick_stream(b, cuda_stream);
+  K4Params k4;
+  memset(&k4, 0, sizeof(k4));
+  k4.g = b->g;
+  k4.st = b->st;
+  k4.n_streams = b->n;
+  k4.hist = b->d_hist[b->hist_cur];
+  k4.hist_stride = b->hist_stride;
+  k4.in = nullptr;
+  k4.frames = 0;
+  k4.speeds = nullptr;
+  k4.flush = 1;
+  k4.out = b->d_out;
+  k4.out_capacity = b->out_capacity;
+  k4.threads_per_stream = b->cfg.threads_per_stream;
+  CU_TRY(launch_k4(k4, st));
+  return 1;
+}
+
+int speedyBatchReadDevice(speedyBatch b, int16_t* d_out, int64_t stride_frames, int32_t* d_counts,
+                          void* cuda_stream) {
+  if (!b) return 0;
+  CU_TRY(cudaSetDevice(b->cfg.device));
+  cudaStream_t st = pick_stream(b, cuda_stream);
+  if (d_out) {
+    dim3 grid(32, b->n);
+    read_copy_kernel<<<grid, 256, 0, st>>>(b->d_out, b->out_capacity, b->g.channels, b->st.out_count, d_out,
+                                           stride_frames);
+    count_launch();
+  }
+  read_finish_kernel<<<(b->n + 127) / 128, 128, 0, st>>>(b->n, b->st.out_count, b->st.status, d_counts,
+                                                         d_out ? stride_frames : (1LL << 40));
+  count_launch();
+  CU_TRY(cudaGetLastError());
+  return 1;
+}
+
+int speedyBatchPeekOutputDevice(speedyBatch b, const int16_t** d_out, const int32_t** d_counts,
+                                int64_t* capacity_frames) {
+  if (!b) return 0;
+  if (d_out) *d_out = b->d_out;
+  if (d_counts) *d_counts = b->st.out_count;
+  if (capacity_frames) *capacity_frames = b->out_capacity;
+  return 1;
+}
+
+int speedyBatchDiscardOutput(speedyBatch b, void* cuda_stream) {
+  return speedyBatchReadDevice(b, nullptr, 0, nullptr, cuda_stream);
+}
+
+// ---- host-pointer variants ------------------------------------------------
+
+static int ensure_stage(speedyBatch b, int64_t frames) {
+  if (b->d_stage && b->stage_frames >= frames) return 1;
+  int16_t* d = nullptr;
+  const long long want = b->cfg.max_write_frames;
+  if (!dev_alloc(b, &d, (size_t)b->n * want * b->g.channels)) return 0;
+  b->d_stage = d;
+  b->stage_frames = want;
+  return 1;
+}
+
+int speedyBatchWrite(speedyBatch b, const int16_t* h_in, int64_t stride_frames, int64_t frames,
+                     const int32_t* h_counts) {
+  if (!b) return 0;
+  if (frames <= 0) return frames == 0;
+  if (frames > b->cfg.max_write_frames) {
+    set_error("speedyBatchWrite: frames exceeds max_write_frames");
+    return 0;
+  }
+  CU_TRY(cudaSetDevice(b->cfg.device));
+  if (!ensure_stage(b, frames)) return 0;
+  cudaStream_t st = b->own_stream;
+  const size_t row = (size_t)frames * b->g.channels * sizeof(int16_t);
+  CU_TRY(cudaMemcpy2DAsync(b->d_stage, row, h_in, (size_t)stride_frames * b->g.channels * sizeof(int16_t), row,
+                           b->n, cudaMemcpyHostToDevice, st));
+  const int32_t* d_counts = nullptr;
+  if (h_counts) {
+    CU_TRY(cudaMemcpyAsync(b->d_counts_stage, h_counts, sizeof(int32_t) * b->n, cudaMemcpyHostToDevice, st));
+    d_counts = b->d_counts_stage;
+  }
+  if (!speedyBatchWriteDevice(b, b->d_stage, frames, frames, d_counts, st)) return 0;
+  CU_TRY(cudaStreamSynchronize(st));
+  return 1;
+}
+
+int speedyBatchFlush(speedyBatch b) {
+  if (!b) return 0;
+  if (!speedyBatchFlushDevice(b, b->own_stream)) return 0;
+  CU_TRY(cudaStreamSynchronize(b->own_stream));
+  return 1;
+}
+
+int speedyBatchRead(speedyBatch b, int16_t* h_out, int64_t stride_frames, int32_t* h_counts) {
+  if (!b) return 0;
+  CU_TRY(cudaSetDevice(b->cfg.device));
+  cudaStream_t st = b->own_stream;
+  CU_TRY(cudaMemcpyAsync(b->h_pinned_counts, b->st.out_count, sizeof(int32_t) * b->n, cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  long long mx = 0;
+  for (int s = 0; s < b->n; s++) {
+    long long c = b->h_pinned_counts[s];
+    if (c > stride_frames) c = stride_frames;
+    if (h_counts) h_counts[s] = (int32_t)c;
+    if (c > mx) mx = c;
+  }
+  if (mx > 0 && h_out) {
+    const size_t row = (size_t)mx * b->g.channels * sizeof(int16_t);
+    CU_TRY(cudaMemcpy2DAsync(h_out, (size_t)stride_frames * b->g.channels * sizeof(int16_t), b->d_out,
+                             (size_t)b->out_capacity * b->g.channels * sizeof(int16_t), row, b->n,
+                             cudaMemcpyDeviceToHost, st));
+  }
+  read_finish_kernel<<<(b->n + 127) / 128, 128, 0, st>>>(b->n, b->st.out_count, b->st.status, b->d_counts_stage,
+                                                         stride_frames);
+  count_launch();
+  CU_TRY(cudaGetLastError());
+  CU_TRY(cudaStreamSynchronize(st));
+  return 1;
+}
+
+int speedyBatchProcess(speedyBatch b, const int16_t* h_in, int64_t frames, int16_t* h_out,
+                       int64_t out_stride_frames, int32_t* h_out_counts) {
+  if (!b) return 0;
+  if (!speedyBatchReset(b, b->own_stream)) return 0;
+  return speedyBatchWrite(b, h_in, frames, frames, nullptr) && speedyBatchFlush(b) &&
+         speedyBatchRead(b, h_out, out_stride_frames, h_out_counts);
+}
+
+int speedyBatchGetStatus(speedyBatch b, int32_t* status) {
+  if (!b || !status) return 0;
+  CU_TRY(cudaSetDevice(b->cfg.device));
+  CU_TRY(cudaStreamSynchronize(b->own_stream));
+  CU_TRY(cudaMemcpy(status, b->st.status, sizeof(int32_t) * b->n, cudaMemcpyDeviceToHost));
+  return 1;
+}
+
+int speedyBatchGetTaps(speedyBatch b, int64_t max_frames, int32_t* n_analysis, int32_t* n_tension,
+                       float* spectrogram, float* energy, float* features, float* tension, float* speed) {
+  if (!b) return 0;
+  CU_TRY(cudaSetDevice(b->cfg.device));
+  CU_TRY(cudaDeviceSynchronize());
+  const int n = b->n;
+  const long long rows = b->max_new_frames;
+  const long long take = max_frames < rows ? max_frames : rows;
+  auto pull = [&](float* h, const float* d, int width) -> int {
+    if (!h) return 1;
+    if (!d) {
+      set_error("speedyBatchGetTaps: tap was not enabled at creation");
+      return 0;
+    }
+    CU_TRY(cudaMemcpy2D(h, (size_t)max_frames * width * sizeof(float), d, (size_t)rows * width * sizeof(float),
+                        (size_t)take * width * sizeof(float), n, cudaMemcpyDeviceToHost));
+    return 1;
+  };
+  if (!pull(spectrogram, b->d_tap_spec, b->g.fft) || !pull(energy, b->d_tap_energy, 1) ||
+      !pull(features, b->d_tap_features, kFeatureCount) || !pull(tension, b->d_tap_tension, 1) ||
+      !pull(speed, b->d_tap_speed, 1))
+    return 0;
+  if (n_analysis || n_tension) {
+    // frames produced by the last write = f(total) - f(total - frames written)
+    std::vector<long long> tot(n);
+    std::vector<int32_t> cnt(n);
+    CU_TRY(cudaMemcpy(tot.data(), b->st.total, sizeof(long long) * n, cudaMemcpyDeviceToHost));
+    if (b->last_d_counts) {
+      CU_TRY(cudaMemcpy(cnt.data(), b->last_d_counts, sizeof(int32_t) * n, cudaMemcpyDeviceToHost));
+    }
+    for (int s = 0; s < n; s++) {
+      const long long before = tot[s] - (b->last_d_counts ? cnt[s] : b->last_frames);
+      const int a1 = frames_analyzed(b->g, tot[s]);
+      const int a0 = frames_analyzed(b->g, before);
+      if (n_analysis) n_analysis[s] = a1 - a0;
+      if (n_tension) n_tension[s] = tensions_ready(b->g, a1) - tensions_ready(b->g, a0);
+    }
+  }
+  return 1;
+}
+
+int speedyBatchSynthDevice(int16_t* d_out, uint64_t first_id, int32_t num_streams, int32_t sample_rate,
+                           int32_t channels, int64_t frames, void* cuda_stream) {
+  if (!d_out || num_streams < 1 || frames < 1) return 0;
+  long long blocks = (frames + 255) / 256;
+  if (blocks > 1024) blocks = 1024;
+  dim3 grid((unsigned)blocks, num_streams);
+  synth_kernel<<<grid, 256, 0, (cudaStream_t)cuda_stream>>>(d_out, first_id, sample_rate, channels, frames);
+  count_launch();
+  CU_TRY(cudaGetLastError());
+  return 1;
+}
+
+}  // extern "C"

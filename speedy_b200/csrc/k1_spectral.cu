@@ -1,0 +1,546 @@
+// K1 — per-frame windowed spectrogram, frame energy and raw spectral difference.
+//
+// Replaces, for every analysis window k of every stream:
+//   speedyAddDataShort          speedy.c:553-565   int16 -> float (/32768)
+//   speedyPreemphasisFilter     speedy.c:416-425   y = x - 0.97*state (double)
+//   speedySpectrogram           speedy.c:438-454   Hamming, zero-pad, FFT, |X|
+//   speedyComputeLocalEnergy    speedy.c:513-516   E = sum_{i=1}^{N/2-1} |X_i|^2
+//   speedyNormalizeByEnergy     speedy.c:628-647   (both frames)
+//   speedyComputeSpectralDiff.  speedy.c:705-719   thresholded sum |log ratio|
+// The low-energy gate, both low-pass recurrences, hysteresis, tension and speed
+// are K2 (k2_tension.cu): they need values from up to Future frames ahead.
+//
+// The local spectral difference of at_time a depends only on the spectra of
+// windows a-1 and a-2, so it is computed here, eagerly, instead of Future
+// frames later as the reference does; the spectrogram never goes to HBM
+// (8 bytes per 10 ms frame do: energy and difference).
+//
+// 16 kHz fast path (N = 480): one warp owns a run of consecutive windows of one
+// stream.  The zero-padded real 480-point transform is computed as two
+// 120-point complex FFTs (even/odd output bins of the packed half-length
+// sequence z[m] = v[2m] + i v[2m+1]) followed by the real-FFT split; each
+// 120-point FFT is radix-8 x radix-15 (the 15 as a 3x5 prime-factor butterfly),
+// entirely in registers with one shared-memory transpose.  Two windows are in
+// flight per warp so that both butterfly passes fill the warp: 2 x 30 radix-8
+// butterflies, then 32 radix-15 butterflies.
+//
+// Any other rate (N = 660, 720, 1440, ...) goes through the generic kernel: one
+// CTA per run, a mixed-radix Stockham FFT in shared memory.
+#include "kernels.cuh"
+
+namespace speedy {
+
+namespace {
+
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ float2 cscale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
+// a * (-i)
+__device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }
+
+__device__ __forceinline__ void dft4(float2& a0, float2& a1, float2& a2, float2& a3) {
+  float2 t0 = cadd(a0, a2), t1 = csub(a0, a2);
+  float2 t2 = cadd(a1, a3), t3 = mul_mi(csub(a1, a3));
+  a0 = cadd(t0, t2);
+  a1 = cadd(t1, t3);
+  a2 = csub(t0, t2);
+  a3 = csub(t1, t3);
+}
+
+// In-place forward 8-point DFT, natural order in and out.
+__device__ __forceinline__ void dft8(float2 (&a)[8]) {
+  float2 e0 = a[0], e1 = a[2], e2 = a[4], e3 = a[6];
+  float2 o0 = a[1], o1 = a[3], o2 = a[5], o3 = a[7];
+  dft4(e0, e1, e2, e3);
+  dft4(o0, o1, o2, o3);
+  const float h = 0.70710678118654752440f;
+  // W8^1 = h(1 - i), W8^2 = -i, W8^3 = h(-1 - i)
+  float2 w1 = make_float2(h * (o1.x + o1.y), h * (o1.y - o1.x));
+  float2 w2 = mul_mi(o2);
+  float2 w3 = make_float2(h * (o3.y - o3.x), -h * (o3.x + o3.y));
+  a[0] = cadd(e0, o0);  a[4] = csub(e0, o0);
+  a[1] = cadd(e1, w1);  a[5] = csub(e1, w1);
+  a[2] = cadd(e2, w2);  a[6] = csub(e2, w2);
+  a[3] = cadd(e3, w3);  a[7] = csub(e3, w3);
+}
+
+__device__ __forceinline__ void dft3(float2& a0, float2& a1, float2& a2) {
+  const float s = 0.86602540378443864676f;  // sin(2pi/3)
+  float2 t = cadd(a1, a2);
+  float2 m = make_float2(a0.x - 0.5f * t.x, a0.y - 0.5f * t.y);
+  float2 d = cscale(csub(a1, a2), s);
+  float2 mi = mul_mi(d);  // -i * s * (a1 - a2)
+  a0 = cadd(a0, t);
+  a1 = cadd(m, mi);
+  a2 = csub(m, mi);
+}
+
+__device__ __forceinline__ void dft5(float2& a0, float2& a1, float2& a2, float2& a3, float2& a4) {
+  const float c1 = 0.30901699437494742410f;   // cos(2pi/5)
+  const float c2 = -0.80901699437494742410f;  // cos(4pi/5)
+  const float s1 = 0.95105651629515357212f;   // sin(2pi/5)
+  const float s2 = 0.58778525229247312917f;   // sin(4pi/5)
+  float2 t1 = cadd(a1, a4), t2 = cadd(a2, a3);
+  float2 t3 = csub(a1, a4), t4 = csub(a2, a3);
+  float2 m1 = make_float2(a0.x + c1 * t1.x + c2 * t2.x, a0.y + c1 * t1.y + c2 * t2.y);
+  float2 m2 = make_float2(a0.x + c2 * t1.x + c1 * t2.x, a0.y + c2 * t1.y + c1 * t2.y);
+  float2 u1 = mul_mi(make_float2(s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y));
+  float2 u2 = mul_mi(make_float2(s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y));
+  a0 = make_float2(a0.x + t1.x + t2.x, a0.y + t1.y + t2.y);
+  a1 = cadd(m1, u1);
+  a4 = csub(m1, u1);
+  a2 = cadd(m2, u2);
+  a3 = csub(m2, u2);
+}
+
+// Forward 15-point DFT as a 3 x 5 prime-factor (Good-Thomas) butterfly:
+// n = (5 n1 + 3 n2) mod 15, k = (10 k1 + 6 k2) mod 15, no inner twiddles.
+__device__ __forceinline__ void dft15(const float2 (&in)[15], float2 (&out)[15]) {
+  float2 t[3][5];
+#pragma unroll
+  for (int n2 = 0; n2 < 5; n2++) {
+    float2 x0 = in[(3 * n2) % 15], x1 = in[(5 + 3 * n2) % 15], x2 = in[(10 + 3 * n2) % 15];
+    dft3(x0, x1, x2);
+    t[0][n2] = x0; t[1][n2] = x1; t[2][n2] = x2;
+  }
+#pragma unroll
+  for (int k1 = 0; k1 < 3; k1++) {
+    dft5(t[k1][0], t[k1][1], t[k1][2], t[k1][3], t[k1][4]);
+#pragma unroll
+    for (int k2 = 0; k2 < 5; k2++) out[(10 * k1 + 6 * k2) % 15] = t[k1][k2];
+  }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// speedy.c:641-642: inverse_norm = 1.0 / (sqrt(energy) + eps), double, stored float.
+__device__ __forceinline__ float inverse_norm(float energy) {
+  const float eps = 2.2204e-16f;
+  return (float)(1.0 / (sqrt((double)energy) + (double)eps));
+}
+
+// speedy.c:705-719 for `half` bins held in shared memory (bin 0 skipped).
+// cur/last: magnitudes of at_time a and a-1; e_cur/e_last their energies; mx the
+// largest magnitude of cur over bins 1..half-1.
+__device__ __forceinline__ float spectral_difference(const float* cur, const float* last, int half,
+                                                     float e_cur, float e_last, float mx, int lane) {
+  const float eps = 2.2204e-16f;
+  const float inv_c = inverse_norm(e_cur);
+  const float inv_l = inverse_norm(e_last);
+  const float thr = (float)((double)mx / 100.0);
+  float acc = 0.0f;
+  for (int i = 1 + lane; i < half; i += 32) {
+    float c = cur[i], l = last[i];
+    if (c > thr && l > thr) {
+      float ratio = __fdiv_rn(__fadd_rn(__fmul_rn(c, inv_c), eps), __fadd_rn(__fmul_rn(l, inv_l), eps));
+      acc += fabsf(logf(ratio));
+    }
+  }
+  return warp_sum(acc);
+}
+
+// ---------------------------------------------------------------------------
+// 16 kHz fast path
+// ---------------------------------------------------------------------------
+constexpr int W16 = 240;            // window
+constexpr int S16 = 160;            // step
+constexpr int P16 = 80;             // window - step
+constexpr int H16 = 240;            // N/2 bins kept
+constexpr int kRun = K1_RUN;        // new windows per warp (plus one halo)
+constexpr int kSampN = (kRun + 1) * S16 + P16;
+
+struct WarpSmem480 {
+  float2 z[2][240];      // per slot: windowed input (aliased), then transposes
+  float mag[3][240];     // previous, slot A, slot B
+  short samp[kSampN + 8];
+};
+
+}  // namespace
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k1_spectral_480(K1Params p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* s_win = reinterpret_cast<float*>(smem_raw);                 // [240]
+  float2* s_tw480 = reinterpret_cast<float2*>(s_win + 240);         // [240]
+  WarpSmem480* s_warp = reinterpret_cast<WarpSmem480*>(s_tw480 + 240);
+
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 240; i += WARPS * 32) {
+    s_win[i] = p.window[i];
+    s_tw480[i] = p.tw_n[i];  // W_480^k
+  }
+  __syncthreads();
+
+  const long long item = (long long)blockIdx.x * WARPS + warp;
+  const int s = (int)(item / p.runs_per_stream);
+  const int run = (int)(item % p.runs_per_stream);
+  if (s >= p.n_streams) return;
+
+  const Geometry& g = p.g;
+  const long long t_old = p.st.total[s];
+  const long long t_new = t_old + (p.counts ? p.counts[s] : p.frames);
+  const int kA = frames_analyzed(g, t_old);
+  const int kB = frames_analyzed(g, t_new);
+  const int k0 = kA + run * kRun;  // first new window of this run
+  if (k0 >= kB) return;
+  const int k1 = min(k0 + kRun, kB);
+
+  Source src;
+  src.channels = g.channels;
+  src.hist = p.hist + (size_t)s * p.hist_stride;
+  src.in = p.in ? p.in + (size_t)s * p.in_stride_frames * g.channels : nullptr;
+  src.hist_base = p.st.hist_base[s];
+  src.t_old = t_old;
+  src.t_new = t_new;
+
+  WarpSmem480& ws = s_warp[warp];
+
+  // Stage the run's samples (mono down-mix) once: windows k0-1 .. k1-1.
+  const long long base = (long long)(k0 - 1) * S16;
+  const int need = (k1 - k0 + 1) * S16 + P16;
+  for (int i = lane; i < need; i += 32) ws.samp[i] = (short)src.mono(base + i);
+  __syncwarp();
+
+  // Per-lane constants.
+  // pass 1: lane = q*15 + m2 handles the radix-8 butterfly of residue m2 of FFT q
+  const int q1 = lane / 15, m2 = lane % 15;
+  float2 tw[8];  // W_240^{m2 (2 j1 + q)}
+#pragma unroll
+  for (int j1 = 0; j1 < 8; j1++) tw[j1] = p.tw_half[(m2 * (2 * j1 + q1)) % 240];
+  // pass 2: lane = slot*16 + q*8 + j1 handles one radix-15 butterfly
+  const int slot2 = lane >> 4, q2 = (lane >> 3) & 1, j1_2 = lane & 7;
+
+  int ip = 0, ia = 1, ib = 2;  // rotating indices into ws.mag
+  float e_prev = 0.0f;
+
+  // windows are processed in pairs (kk, kk+1), starting at the halo k0-1
+  for (int kk = k0 - 1; kk < k1; kk += 2) {
+    // ---- pass 0: int16 -> float, pre-emphasis (double), Hamming ----------
+#pragma unroll
+    for (int slot = 0; slot < 2; slot++) {
+      const int k = kk + slot;
+      const int o = (k - (k0 - 1)) * S16;
+      float* v = reinterpret_cast<float*>(ws.z[slot]);
+      const bool live = (k >= 0) && (k < k1);
+      for (int n = lane; n < W16; n += 32) {
+        float out = 0.0f;
+        if (live) {
+          // state entering sample 0 is the last sample of the previous window,
+          // i.e. sample P-1 of this one (speedy.c:416-425; window k-1 ends at
+          // k*S + P - 1); 0 before the first window.
+          int xp = (n > 0) ? ws.samp[o + n - 1] : (k >= 1 ? ws.samp[o + P16 - 1] : 0);
+          int xc = ws.samp[o + n];
+          double fc = (double)((float)xc * 3.0517578125e-05f);
+          double fp = (double)((float)xp * 3.0517578125e-05f);
+          float y = (float)__dsub_rn(fc, __dmul_rn(0.97, fp));
+          out = __fmul_rn(y, s_win[n]);
+        }
+        v[n] = out;
+      }
+    }
+    __syncwarp();
+
+    // ---- pass 1: radix-8 butterflies, 30 lanes, one slot at a time --------
+#pragma unroll
+    for (int slot = 0; slot < 2; slot++) {
+      float2 a[8];
+      if (lane < 30) {
+        const float2* zin = ws.z[slot];
+#pragma unroll
+        for (int m1 = 0; m1 < 8; m1++) a[m1] = zin[15 * m1 + m2];  // z[m] = (v[2m], v[2m+1])
+      }
+      __syncwarp();
+      if (lane < 30) {
+        if (q1) {
+          // odd output bins: z[m] * W_240^m = z[m] * W_16^{m1} * W_240^{m2};
+          // W_240^{m2} is folded into tw[], W_16^{m1} applied here.
+          const float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f;
+          const float h = 0.70710678118654752440f;
+          a[1] = cmul(a[1], make_float2(c1, -s1));
+          a[2] = cmul(a[2], make_float2(h, -h));
+          a[3] = cmul(a[3], make_float2(s1, -c1));
+          a[4] = mul_mi(a[4]);
+          a[5] = cmul(a[5], make_float2(-s1, -c1));
+          a[6] = cmul(a[6], make_float2(-h, -h));
+          a[7] = cmul(a[7], make_float2(-c1, -s1));
+        }
+        dft8(a);
+        float2* zout = ws.z[slot];
+#pragma unroll
+        for (int j1 = 0; j1 < 8; j1++) zout[(q1 * 8 + j1) * 15 + m2] = cmul(a[j1], tw[j1]);
+      }
+    }
+    __syncwarp();
+
+    // ---- pass 2: radix-15 butterflies, 32 lanes ----------------------------
+    {
+      float2 b[15], c[15];
+      const float2* zin = ws.z[slot2] + (q2 * 8 + j1_2) * 15;
+#pragma unroll
+      for (int i = 0; i < 15; i++) b[i] = zin[i];
+      dft15(b, c);
+      __syncwarp();
+      // Z[kbin], kbin = 2 (j1 + 8 j2) + q : even bins from FFT 0, odd from FFT 1
+      float2* zout = ws.z[slot2];
+#pragma unroll
+      for (int j2 = 0; j2 < 15; j2++) zout[2 * (j1_2 + 8 * j2) + q2] = c[j2];
+    }
+    __syncwarp();
+
+    // ---- real-FFT split, magnitude, energy ---------------------------------
+    float e_slot[2], mx_slot[2];
+#pragma unroll
+    for (int slot = 0; slot < 2; slot++) {
+      const float2* Z = ws.z[slot];
+      float* mag = ws.mag[slot == 0 ? ia : ib];
+      float e = 0.0f, mx = 0.0f;
+      for (int kb = lane; kb < H16; kb += 32) {
+        float2 zk = Z[kb];
+        float2 zm = Z[(240 - kb) % 240];
+        float2 zc = make_float2(zm.x, -zm.y);
+        float2 sum = cscale(cadd(zk, zc), 0.5f);
+        float2 dif = cscale(csub(zk, zc), 0.5f);
+        float2 wd = mul_mi(cmul(s_tw480[kb], dif));
+        float re = sum.x + wd.x, im = sum.y + wd.y;
+        // speedy.c:434-436: sqrt(r*r + i*i), products and sum rounded to float
+        float m = __fsqrt_rn(__fadd_rn(__fmul_rn(re, re), __fmul_rn(im, im)));
+        mag[kb] = m;
+        if (kb >= 1) {
+          e += m * m;
+          mx = fmaxf(mx, m);
+        }
+      }
+      e_slot[slot] = warp_sum(e);
+      mx_slot[slot] = warp_max(mx);
+    }
+    __syncwarp();
+
+    // ---- spectral difference against the previous window, outputs ---------
+#pragma unroll
+    for (int slot = 0; slot < 2; slot++) {
+      const int k = kk + slot;
+      const float* cur = ws.mag[slot == 0 ? ia : ib];
+      const float* last = ws.mag[slot == 0 ? ip : ia];
+      const float e_last = slot == 0 ? e_prev : e_slot[0];
+      if (k >= k0 && k < k1) {
+        float lsd = spectral_difference(cur, last, H16, e_slot[slot], e_last, mx_slot[slot], lane);
+        const int j = k - kA;
+        if (lane == 0) p.feat[(size_t)j * p.n_streams + s] = make_float2(e_slot[slot], lsd);
+        if (p.tap_spec) {
+          float* row = p.tap_spec + ((size_t)s * p.tap_stride + j) * 480;
+          for (int i = lane; i < 240; i += 32) {
+            row[i] = cur[i];
+            if (i >= 1) row[480 - i] = cur[i];
+          }
+          if (lane == 0) {
+            float2 z0 = ws.z[slot][0];  // X[N/2] = Re(Z0) - Im(Z0)
+            row[240] = fabsf(z0.x - z0.y);
+          }
+        }
+      }
+    }
+    e_prev = e_slot[1];
+    // rotate: slot B becomes "previous"
+    int t = ip; ip = ib; ib = ia; ia = t;
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Generic path: any N = 2W whose prime factors are small.  One CTA per run.
+// ---------------------------------------------------------------------------
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k1_spectral_generic(K1Params p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const Geometry& g = p.g;
+  const int N = g.fft, W = g.window, S = g.step, P = g.partial, half = N / 2;
+  float2* bufA = reinterpret_cast<float2*>(smem_raw);  // [N]
+  float2* bufB = bufA + N;                              // [N]
+  float* mag0 = reinterpret_cast<float*>(bufB + N);     // [half]
+  float* mag1 = mag0 + half;                            // [half]
+  float* red = mag1 + half;                             // [64]
+  __shared__ float s_e, s_mx, s_lsd;
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const long long item = blockIdx.x;
+  const int s = (int)(item / p.runs_per_stream);
+  const int run = (int)(item % p.runs_per_stream);
+  if (s >= p.n_streams) return;
+
+  const long long t_old = p.st.total[s];
+  const long long t_new = t_old + (p.counts ? p.counts[s] : p.frames);
+  const int kA = frames_analyzed(g, t_old);
+  const int kB = frames_analyzed(g, t_new);
+  const int k0 = kA + run * kRun;
+  if (k0 >= kB) return;
+  const int k1 = min(k0 + kRun, kB);
+
+  Source src;
+  src.channels = g.channels;
+  src.hist = p.hist + (size_t)s * p.hist_stride;
+  src.in = p.in ? p.in + (size_t)s * p.in_stride_frames * g.channels : nullptr;
+  src.hist_base = p.st.hist_base[s];
+  src.t_old = t_old;
+  src.t_new = t_new;
+
+  float* cur = mag0;
+  float* last = mag1;
+  float e_last = 0.0f;
+  for (int k = k0 - 1; k < k1; k++) {
+    // window, zero-pad
+    const long long f0 = (long long)k * S;
+    for (int n = tid; n < N; n += THREADS) {
+      float out = 0.0f;
+      if (n < W && k >= 0) {
+        int xp = (n > 0) ? src.mono(f0 + n - 1) : (k >= 1 ? src.mono(f0 + P - 1) : 0);
+        int xc = src.mono(f0 + n);
+        double fc = (double)((float)xc * 3.0517578125e-05f);
+        double fp = (double)((float)xp * 3.0517578125e-05f);
+        float y = (float)__dsub_rn(fc, __dmul_rn(0.97, fp));
+        out = __fmul_rn(y, p.window[n]);
+      }
+      bufA[n] = make_float2(out, 0.0f);
+    }
+    __syncthreads();
+    // Stockham stages: y[q + s(Rp + t)] = W_n^{pt} sum_r x[q + s(p + r m)] W_R^{rt}
+    float2* x = bufA;
+    float2* y = bufB;
+    int n = N, st = 1;
+    for (int f = 0; f < p.n_factors; f++) {
+      const int R = p.factors[f];
+      const int m = n / R;
+      const int total = m * st * R;  // == N: one thread per output
+      for (int o = tid; o < total; o += THREADS) {
+        const int q = o % st;
+        const int t = (o / st) % R;
+        const int pp = o / (st * R);
+        float2 acc = make_float2(0.0f, 0.0f);
+        for (int r = 0; r < R; r++) {
+          float2 a = x[q + st * (pp + r * m)];
+          float2 w = p.tw_n[(N / R) * ((r * t) % R)];
+          acc = cadd(acc, cmul(a, w));
+        }
+        acc = cmul(acc, p.tw_n[(int)(((long long)pp * t * st) % N)]);
+        y[q + st * (R * pp + t)] = acc;
+      }
+      __syncthreads();
+      float2* tmp = x; x = y; y = tmp;
+      n = m;
+      st *= R;
+    }
+    // magnitude, energy, max
+    float e = 0.0f, mx = 0.0f;
+    for (int i = tid; i < half; i += THREADS) {
+      float2 c = x[i];
+      float mg = __fsqrt_rn(__fadd_rn(__fmul_rn(c.x, c.x), __fmul_rn(c.y, c.y)));
+      cur[i] = mg;
+      if (i >= 1) {
+        e += mg * mg;
+        mx = fmaxf(mx, mg);
+      }
+    }
+    e = warp_sum(e);
+    mx = warp_max(mx);
+    if (lane == 0) { red[warp] = e; red[32 + warp] = mx; }
+    __syncthreads();
+    if (tid == 0) {
+      float es = 0.0f, ms = 0.0f;
+      for (int w = 0; w < THREADS / 32; w++) { es += red[w]; ms = fmaxf(ms, red[32 + w]); }
+      s_e = es; s_mx = ms;
+    }
+    __syncthreads();
+    const float e_cur = s_e, mx_cur = s_mx;
+    if (k >= k0) {
+      // spectral difference: every warp takes a slice of the bins
+      const float eps = 2.2204e-16f;
+      const float inv_c = inverse_norm(e_cur), inv_l = inverse_norm(e_last);
+      const float thr = (float)((double)mx_cur / 100.0);
+      float acc = 0.0f;
+      for (int i = 1 + tid; i < half; i += THREADS) {
+        float c = cur[i], l = last[i];
+        if (c > thr && l > thr) {
+          float ratio = __fdiv_rn(__fadd_rn(__fmul_rn(c, inv_c), eps), __fadd_rn(__fmul_rn(l, inv_l), eps));
+          acc += fabsf(logf(ratio));
+        }
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) red[warp] = acc;
+      __syncthreads();
+      if (tid == 0) {
+        float t = 0.0f;
+        for (int w = 0; w < THREADS / 32; w++) t += red[w];
+        s_lsd = t;
+      }
+      __syncthreads();
+      const int j = k - kA;
+      if (tid == 0) p.feat[(size_t)j * p.n_streams + s] = make_float2(e_cur, s_lsd);
+      if (p.tap_spec) {
+        float* row = p.tap_spec + ((size_t)s * p.tap_stride + j) * N;
+        for (int i = tid; i < N; i += THREADS) {
+          float2 c = x[i];
+          row[i] = __fsqrt_rn(__fadd_rn(__fmul_rn(c.x, c.x), __fmul_rn(c.y, c.y)));
+        }
+      }
+    }
+    __syncthreads();
+    e_last = e_cur;
+    float* tmp = cur; cur = last; last = tmp;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Host-side launch
+// ---------------------------------------------------------------------------
+size_t k1_smem_bytes_480(int warps) {
+  return 240 * sizeof(float) + 240 * sizeof(float2) + (size_t)warps * sizeof(WarpSmem480);
+}
+
+cudaError_t launch_k1(const K1Params& p, cudaStream_t stream) {
+  if (p.max_new_frames <= 0) return cudaSuccess;
+  K1Params q = p;
+  q.runs_per_stream = (p.max_new_frames + kRun - 1) / kRun;
+  const long long items = (long long)q.runs_per_stream * p.n_streams;
+  if (p.g.fft == 480) {
+    constexpr int WARPS = 4;
+    const size_t smem = k1_smem_bytes_480(WARPS);
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(k1_spectral_480<WARPS>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      attr_set = true;
+    }
+    const unsigned blocks = (unsigned)((items + WARPS - 1) / WARPS);
+    k1_spectral_480<WARPS><<<blocks, WARPS * 32, smem, stream>>>(q);
+  } else {
+    constexpr int THREADS = 128;
+    const int N = p.g.fft;
+    const size_t smem = 2 * (size_t)N * sizeof(float2) + (size_t)N * sizeof(float) + 64 * sizeof(float);
+    static int attr_smem = 0;
+    if ((int)smem > attr_smem) {
+      cudaError_t e = cudaFuncSetAttribute(k1_spectral_generic<THREADS>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      attr_smem = (int)smem;
+    }
+    k1_spectral_generic<THREADS><<<(unsigned)items, THREADS, smem, stream>>>(q);
+  }
+  count_launch();
+  return cudaGetLastError();
+}
+
+}  // namespace speedy

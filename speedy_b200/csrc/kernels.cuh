@@ -1,0 +1,101 @@
+// Kernel parameter blocks and host-side launchers (one .cu per kernel family).
+#pragma once
+
+#include "common.cuh"
+
+#ifndef K1_RUN
+#define K1_RUN 15  // new analysis windows per warp/CTA (plus one halo window)
+#endif
+
+namespace speedy {
+
+constexpr int kMaxFactors = 16;
+
+void count_launch();
+
+// ---- K1: spectrogram, frame energy, raw spectral difference ---------------
+struct K1Params {
+  Geometry g;
+  StreamState st;
+  int n_streams;
+  // input of this write
+  const int16_t* hist;           // [n][hist_stride] carried tail (current buffer)
+  long long hist_stride;         // int16 elements per stream
+  const int16_t* in;             // caller's device buffer (may be null if frames == 0)
+  long long in_stride_frames;
+  const int32_t* counts;         // optional per-stream frame counts
+  long long frames;              // uniform frame count
+  // per-call scratch out: [max_new_frames][n] (energy, raw spectral difference)
+  float2* feat;
+  int max_new_frames;
+  int runs_per_stream;           // filled by the launcher
+  // tables
+  const float* window;           // [W] Hamming (speedy.c:256-258)
+  const float2* tw_n;            // [N] W_N^k
+  const float2* tw_half;         // [N/2] W_{N/2}^k
+  int n_factors;
+  int factors[kMaxFactors];      // generic path: radices of N
+  // optional tap: [n][tap_stride][N]
+  float* tap_spec;
+  int tap_stride;
+};
+cudaError_t launch_k1(const K1Params& p, cudaStream_t stream);
+
+// ---- K2/K3: recurrences, hysteresis, tension, speed ------------------------
+struct K2Params {
+  Geometry g;
+  StreamState st;
+  int n_streams;
+  const int32_t* counts;
+  long long frames;
+  const float2* feat;            // from K1
+  int max_new_frames;
+  float* speeds;                 // out: [n][speeds_stride]
+  int speeds_stride;
+  const float* override_speeds;  // optional [n][override_stride], indexed by tension frame
+  long long override_stride;
+  // optional taps, rows indexed by the j-th new tension of this write
+  float* tap_features;           // [n][max_new_frames][15]
+  float* tap_tension;            // [n][max_new_frames]
+  float* tap_speed;              // [n][max_new_frames]
+  float* tap_energy;             // [n][max_new_frames] by new analysis frame
+};
+cudaError_t launch_k2(const K2Params& p, cudaStream_t stream);
+
+// ---- K4: Sonic AMDF pitch search + overlap-add ----------------------------
+struct K4Params {
+  Geometry g;
+  StreamState st;
+  int n_streams;
+  const int16_t* hist;
+  long long hist_stride;
+  const int16_t* in;
+  long long in_stride_frames;
+  const int32_t* counts;
+  long long frames;
+  const float* speeds;           // from K2
+  int speeds_stride;
+  int flush;                     // 1: this launch is sonicFlushStream
+  int16_t* out;                  // [n][out_capacity][C]
+  long long out_capacity;        // sample frames per stream
+  int threads_per_stream;
+  int buf_frames;                // shared-memory window, filled by the launcher
+};
+cudaError_t launch_k4(const K4Params& p, cudaStream_t stream);
+
+// ---- bookkeeping after a write: carry the input tail, advance totals ------
+struct TailParams {
+  Geometry g;
+  StreamState st;
+  int n_streams;
+  const int16_t* hist_src;       // current history buffer
+  int16_t* hist_dst;             // the other one
+  long long hist_stride;
+  const int16_t* in;
+  long long in_stride_frames;
+  const int32_t* counts;
+  long long frames;
+};
+cudaError_t launch_tail(const TailParams& p, cudaStream_t stream);
+
+}  // namespace speedy

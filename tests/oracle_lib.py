@@ -210,6 +210,18 @@ def synth(first_id, n_streams, rate, channels, n_frames):
     return out
 
 
+def default_out_cap(n, speed, nonlinear, g):
+    """Output frames that always suffice: speeds never drop below 1 when R_g > 1
+    (speedy.c:774) and never below kMinimumSpeed = 0.01 otherwise (speedy.c:776)."""
+    if speed > 1.0:
+        worst = 1.0
+    elif nonlinear != 0:
+        worst = 0.01
+    else:
+        worst = speed
+    return int(n / worst * 1.02) + 4 * g.max_required
+
+
 def port_process(c, pcm, speed_override=None, taps=True, out_cap=None):
     """Run one stream through the restatement.  pcm: int16 [frames, channels]
     (or [frames] for mono).  Returns dict(out, spectrogram, energy, normalized,
@@ -220,7 +232,7 @@ def port_process(c, pcm, speed_override=None, taps=True, out_cap=None):
     nA = port().oracle_frames_analyzed(C.byref(g), n)
     nT = port().oracle_tensions_ready(C.byref(g), nA)
     if out_cap is None:
-        out_cap = int(n / max(min(c.speed, 1.0), 0.01) * 1.1) + 4 * g.max_required
+        out_cap = default_out_cap(n, c.speed, c.nonlinear, g)
     out = np.zeros((out_cap, c.channels), dtype=np.int16)
     res = {}
     t = None
@@ -255,7 +267,7 @@ def ref_process(kind, pcm, rate, channels=1, speed=2.0, nonlinear=1.0,
     g = geometry(rate, kind == "kiss")
     maxf = n // g.step + 2
     if out_cap is None:
-        out_cap = int(n / max(min(speed, 1.0), 0.01) * 1.1) + 4 * g.max_required
+        out_cap = default_out_cap(n, speed, nonlinear, g)
     out = np.zeros((out_cap, channels), dtype=np.int16)
     res = {}
     t = None
