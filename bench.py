@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""Benchmark of the nonlinear speed-up hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # the CUDA path
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the CPU reference arm
+
+Workload (BASELINE.json configs[1], the configuration the metric is quoted on for
+one GPU): 1024 synthetic 16 kHz mono streams x 60 s, nonlinear speed 2.0x, per GPU
+(weak scaling: streams are independent, every rank gets its own 1024, no
+collective on the data path).  A "step" is one pass of the whole hot path over
+that batch: reset, write all 60 s, flush.
+
+  value  audio-seconds processed per second with the input already in HBM, timed
+         with CUDA events on the launching stream, max over ranks.
+  e2e    the same metric through speedyBatchProcess with HOST (pinned) buffers:
+         host->device and device->host copies inside the timed region.
+  roofline  the dominant kernel's algorithmic bytes / its measured duration
+         against the measured HBM copy bandwidth (MEASURED_PEAKS.json).
+  cpu_baseline  the reference's own speedy.c + soniclib.c (oracle/_ref) on all
+         host cores over a bounded sample of the same streams.
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+RATE = 16000
+CHANNELS = 1
+STREAMS = int(os.environ.get("SPEEDY_BENCH_STREAMS", 1024))
+SECONDS = int(os.environ.get("SPEEDY_BENCH_SECONDS", 60))
+SPEED = 2.0
+NONLINEAR = 1.0
+FEEDBACK = 0.1  # library default (soniclib.c:122)
+WORKLOAD = "%d synthetic 16 kHz mono streams x %d s, nonlinear %.1fx, per GPU" % (STREAMS, SECONDS, SPEED)
+METRIC = "batched real-time factor (audio-seconds processed per second)"
+UNIT = "audio-s/s"
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        load = [x for x in sm if x > 0]
+        return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------
+# CPU reference arm
+# --------------------------------------------------------------------------
+def load_reference():
+    """oracle/_ref (the reference's own code); falls back to the restated port."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as ol
+    if ol.ref_available("fftw"):
+        return ol, "reference"
+    return ol, "port"
+
+
+def cpu_run(ol, kind, pcm, threads):
+    """Process pcm [n, frames, 1] on `threads` OS threads; returns seconds."""
+    n, frames, ch = pcm.shape
+    counts = np.zeros(n, np.int64)
+    t0 = time.perf_counter()
+    if kind == "reference":
+        ol.ref("fftw").ref_run_batch(ol.sptr(pcm), frames, n, RATE, ch, SPEED, NONLINEAR, FEEDBACK, 1000, None, 0,
+                                     counts.ctypes.data_as(ol.c_long_p), threads)
+    else:
+        out = np.zeros((n, frames + 4096, ch), np.int16)
+        c = ol.cfg(RATE, ch, SPEED, NONLINEAR, FEEDBACK, False, True)
+        ol.port().oracle_process_batch(ctypes.byref(c), ol.sptr(pcm), frames, n, ol.sptr(out), frames + 4096,
+                                       counts.ctypes.data_as(ol.c_long_p), threads)
+    dt = time.perf_counter() - t0
+    assert counts.min() > 0
+    return dt
+
+
+def cpu_sample(ol, n_streams, seconds):
+    return ol.synth(0, n_streams, RATE, CHANNELS, seconds * RATE)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return 0
+    ol, kind = load_reference()
+    cores = os.cpu_count() or 1
+    # bounded sample: two streams per core of the same synthetic workload per step
+    n = 2 * cores
+    pcm = cpu_sample(ol, n, SECONDS)
+    for _ in range(args.warmup):
+        cpu_run(ol, kind, pcm[:cores], cores)
+    times = [cpu_run(ol, kind, pcm, cores) for _ in range(args.steps)]
+    dt = sum(times) / len(times)
+    value = n * SECONDS / dt
+    sample = "%d of the workload's streams x %d s per step (ids 0..%d), %d threads" % (n, SECONDS, n - 1, cores)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32+i16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "CPU reference: unmodified speedy.c + soniclib.c "
+                   "(FFT and Sonic restated, see oracle/), all host cores, bounded sample"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# --------------------------------------------------------------------------
+# CUDA arm
+# --------------------------------------------------------------------------
+def run_cuda_arm(args):
+    import torch
+    import speedy_b200 as sb
+
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the CUDA arm has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    frames = SECONDS * RATE
+    n = STREAMS
+    out_cap = frames + 4096
+    batch = sb.Batch(n, RATE, CHANNELS, speed=SPEED, nonlinear=NONLINEAR, feedback=FEEDBACK, device=local,
+                     max_write_frames=frames, out_capacity=out_cap, threads_per_stream=args.threads_per_stream)
+    # independent streams, sharded by id: rank r owns ids [r*n, (r+1)*n)
+    # a real (non-default) stream: the library launches on the stream it is given and
+    # torch.cuda.Event only sees torch's current stream, so make them the same one
+    tstream = torch.cuda.Stream()
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    d_in = torch.empty((n, frames, CHANNELS), dtype=torch.int16, device="cuda")
+    sb.synth_device(d_in, rank * n, n, RATE, CHANNELS, frames, stream=stream)
+    torch.cuda.synchronize()
+
+    def step():
+        batch.reset(stream)
+        batch.write_device(d_in, frames, frames, None, stream)
+        batch.flush_device(stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+
+    # ---- timed region: K steps, device-resident input ----------------------
+    batch.set_profiling(True)
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = sb.kernel_launches()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ktimes = []
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    launches = sb.kernel_launches() - launches0
+    elapsed_ms = ev0.elapsed_time(ev1)
+    ktimes.append(batch.kernel_times())
+    clocks = sampler.stop()
+    batch.set_profiling(False)
+
+    # output size of one step (for the algorithmic bytes)
+    d_counts = torch.empty(n, dtype=torch.int32, device="cuda")
+    batch.read_device(None, 0, d_counts, stream)
+    torch.cuda.synchronize()
+    out_frames = int(d_counts.sum().item())
+    status = batch.status()
+    assert not (status & (sb.STATUS_OUTPUT_OVERFLOW | sb.STATUS_INPUT_OVERFLOW)).any(), "stream overflow"
+
+    # ---- end to end: host buffers through speedyBatchProcess ----------------
+    h_in = torch.empty((n, frames, CHANNELS), dtype=torch.int16, pin_memory=True)
+    h_in.copy_(d_in)
+    h_out = torch.empty((n, out_cap, CHANNELS), dtype=torch.int16, pin_memory=True)
+    h_counts = torch.zeros(n, dtype=torch.int32)
+    e2e_steps = max(1, min(args.steps, 5))
+    for _ in range(2):
+        batch.process_ptr(h_in, frames, h_out, out_cap, h_counts)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        batch.process_ptr(h_in, frames, h_out, out_cap, h_counts)
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    e2e_out_frames = int(h_counts.sum().item())
+    assert e2e_out_frames == out_frames, (e2e_out_frames, out_frames)
+
+    # ---- max over ranks -----------------------------------------------------
+    t = torch.tensor([elapsed_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms, e2e_ms = t.tolist()
+    ms_per_step = elapsed_ms / args.steps
+    audio_s = world * n * SECONDS
+    value = audio_s / (ms_per_step / 1e3)
+    e2e_value = audio_s / (e2e_ms / 1e3)
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        kt = ktimes[-1]
+        # the dominant kernel and its algorithmic bytes (2*C bytes read
+        # + 2*C/speed written per input sample frame; the spectral kernel only reads)
+        in_bytes = n * frames * CHANNELS * 2
+        out_bytes = out_frames * CHANNELS * 2
+        alg = {"spectral": in_bytes, "sonic": in_bytes + out_bytes}
+        sonic_ms = kt["sonic"] + kt["flush_sonic"]
+        dominant = "sonic" if sonic_ms >= kt["spectral"] else "spectral"
+        dom_ms = sonic_ms if dominant == "sonic" else kt["spectral"]
+        achieved = alg[dominant] / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0
+        roofline = {
+            "bound": "hbm", "kernel": "k4_sonic" if dominant == "sonic" else "k1_spectral_480",
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": None, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": alg[dominant], "kernel_ms": dom_ms,
+            "kernel_ms_all": kt,
+            "whole_path": {"algorithmic_bytes_per_step": in_bytes + out_bytes,
+                           "achieved": (in_bytes + out_bytes) / (ms_per_step / 1e3) / 1e9,
+                           "frac": (in_bytes + out_bytes) / (ms_per_step / 1e3) / 1e9 / peak},
+        }
+        cpu_baseline = None
+        if world == 1 and not args.no_cpu_baseline:
+            ol, kind = load_reference()
+            cores = os.cpu_count() or 1
+            per_core = 4
+            ns = per_core * cores
+            pcm = h_in[:ns].numpy()
+            if ns > n:
+                pcm = cpu_sample(ol, ns, SECONDS)
+            dt = cpu_run(ol, kind, np.ascontiguousarray(pcm), cores)
+            cpu_baseline = {"value": ns * SECONDS / dt, "unit": UNIT, "cores": cores, "kind": kind,
+                            "sample": "%d of the %d streams x %d s (%.1f s of wall time on %d threads)"
+                                      % (ns, n, SECONDS, dt, cores)}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32+i16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "streams_per_gpu": n, "seconds_per_stream": SECONDS,
+                       "sample_rate": RATE, "channels": CHANNELS, "speed": SPEED, "nonlinear_factor": NONLINEAR,
+                       "feedback_strength": FEEDBACK, "output_frames_per_step": out_frames,
+                       "cache": "inputs (%.2f GB per step) exceed the 126 MB L2" % (in_bytes / 1e9),
+                       "sharding": "independent streams per rank, no collective"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes + 4 * n,
+                    "api": "speedyBatchProcess (pinned host buffers)"},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+            "clocks": clocks,
+            "build": sb.lib().speedyBatchBuildInfo().decode(),
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--threads-per-stream", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_cuda_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

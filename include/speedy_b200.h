@@ -199,6 +199,13 @@ int speedyBatchProcess(speedyBatch batch, const int16_t* h_in, int64_t frames,
                        int16_t* h_out, int64_t out_stride_frames,
                        int32_t* h_out_counts);
 
+/* Per-kernel device timing for benchmarks.  When on, every write/flush brackets
+ * its kernels with CUDA events on the launching stream; GetKernelTimes returns
+ * the milliseconds of {spectral, tension, sonic, tail, flush-sonic} of the last
+ * write and flush (synchronises on those events).  Return 1/0. */
+int speedyBatchSetProfiling(speedyBatch batch, int on);
+int speedyBatchGetKernelTimes(speedyBatch batch, float* ms5);
+
 /* Taps of the LAST write call, copied to host arrays (any may be NULL):
  *   n_analysis[s], n_tension[s]  frames produced by that write
  *   spectrogram [s][max_frames][fft]   row j = j-th new analysis frame

@@ -36,11 +36,6 @@ spectrogramFunction = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.POINTER(C.c_float
 _lib = None
 
 
-def build(force=False, verbose=False):
-    from . import build as _b
-    return _b.build(force=force, verbose=verbose)
-
-
 def lib():
     """The loaded C-ABI library.  Raises if it has not been built."""
     global _lib
@@ -71,6 +66,8 @@ def lib():
         "speedyBatchPeekOutputDevice": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_int64)]),
         "speedyBatchDiscardOutput": (C.c_int, [vp, vp]),
         "speedyBatchProcess": (C.c_int, [vp, i16p, C.c_int64, i16p, C.c_int64, vp]),
+        "speedyBatchSetProfiling": (C.c_int, [vp, C.c_int]),
+        "speedyBatchGetKernelTimes": (C.c_int, [vp, fp]),
         "speedyBatchGetTaps": (C.c_int, [vp, C.c_int64, vp, vp, fp, fp, fp, fp, fp]),
         "speedyBatchGetStatus": (C.c_int, [vp, vp]),
         "speedyBatchFrameGeometry": (C.c_int, [C.c_int, i32p, i32p, i32p]),
@@ -240,6 +237,19 @@ class Batch:
 
     def discard_output(self, stream=None):
         self._ok(lib().speedyBatchDiscardOutput(self.h, stream), "speedyBatchDiscardOutput")
+
+    def set_profiling(self, on):
+        self._ok(lib().speedyBatchSetProfiling(self.h, int(on)), "speedyBatchSetProfiling")
+
+    def kernel_times(self):
+        ms = np.zeros(5, np.float32)
+        self._ok(lib().speedyBatchGetKernelTimes(self.h, ms.ctypes.data), "speedyBatchGetKernelTimes")
+        return dict(zip(("spectral", "tension", "sonic", "tail", "flush_sonic"), ms.tolist()))
+
+    def process_ptr(self, h_in, frames, h_out, out_stride, h_counts):
+        """speedyBatchProcess on raw host addresses (e.g. pinned torch tensors)."""
+        self._ok(lib().speedyBatchProcess(self.h, _ptr(h_in), frames, _ptr(h_out), out_stride, _ptr(h_counts)),
+                 "speedyBatchProcess")
 
     def status(self):
         st = np.zeros(self.n, np.int32)

@@ -5,6 +5,9 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <stdlib.h>
+
+#include <algorithm>
 #include <atomic>
 #include <mutex>
 #include <string>
@@ -211,9 +214,13 @@ struct speedyBatchStruct {
   long long stage_frames;
   int32_t* d_counts_stage;
   int32_t* h_pinned_counts;
-  // child contexts used by speedyBatchProcess
+  // child contexts used by speedyBatchProcess (slabs of streams, pipelined)
   std::vector<speedyBatch> slabs;
-  int16_t* d_slab_in;
+  long long slab_frames;
+  // per-kernel timing (speedyBatchSetProfiling)
+  int profiling;
+  cudaEvent_t ev[6];
+  int ev_recorded;   // 0 none, 1 write, 2 flush
 };
 
 namespace {
@@ -317,6 +324,7 @@ void speedyBatchDestroy(speedyBatch b) {
   for (speedyBatch c : b->slabs) speedyBatchDestroy(c);
   for (void* p : b->allocs) cudaFree(p);
   if (b->h_pinned_counts) cudaFreeHost(b->h_pinned_counts);
+  for (int i = 0; i < 6; i++) if (b->ev[i]) cudaEventDestroy(b->ev[i]);
   if (b->own_stream) cudaStreamDestroy(b->own_stream);
   delete b;
 }
@@ -346,7 +354,10 @@ speedyBatch speedyBatchCreate(const speedyBatchConfig* cfg) {
   b->d_counts_stage = nullptr;
   b->d_override = nullptr;
   b->override_stride = 0;
-  b->d_slab_in = nullptr;
+  b->slab_frames = 0;
+  b->profiling = 0;
+  b->ev_recorded = 0;
+  for (int i = 0; i < 6; i++) b->ev[i] = nullptr;
   b->d_tap_spec = b->d_tap_energy = b->d_tap_features = b->d_tap_tension = b->d_tap_speed = nullptr;
   make_geometry(cfg->sample_rate, cfg->num_channels, cfg->match_matlab, &b->g);
   const Geometry& g = b->g;
@@ -369,7 +380,7 @@ speedyBatch speedyBatchCreate(const speedyBatchConfig* cfg) {
        dev_alloc(b, &s.nonlinear, n) && dev_alloc(b, &s.feedback, n) && dev_alloc(b, &s.lp_energy, n) &&
        dev_alloc(b, &s.lp_diff, n) && dev_alloc(b, &s.cur_dur, n) && dev_alloc(b, &s.des_dur, n) &&
        dev_alloc(b, &s.ring_comp, (size_t)n * kRing) && dev_alloc(b, &s.ring_energy, (size_t)n * kRing) &&
-       dev_alloc(b, &s.ring_lsd, (size_t)n * kRing) && dev_alloc(b, &s.ring_lp, 1) &&
+       dev_alloc(b, &s.ring_lsd, (size_t)n * kRing) &&
        dev_alloc(b, &s.sonic_head, n) && dev_alloc(b, &s.sonic_fed, n) && dev_alloc(b, &s.prev_period, n) &&
        dev_alloc(b, &s.prev_min_diff, n) && dev_alloc(b, &s.remaining_copy, n) &&
        dev_alloc(b, &s.sonic_speed, n) && dev_alloc(b, &s.out_total, n) && dev_alloc(b, &s.out_count, n) &&
@@ -511,6 +522,7 @@ int speedyBatchWriteDevice(speedyBatch b, const int16_t* d_in, int64_t stride_fr
   k1.counts = d_counts;
   k1.frames = frames;
   k1.feat = b->d_feat;
+  k1.feat_stride = b->max_new_frames;
   // at most this many analysis windows can complete in one write
   k1.max_new_frames = (int)(frames / g.step) + 2;
   if (k1.max_new_frames > b->max_new_frames) k1.max_new_frames = b->max_new_frames;
@@ -521,7 +533,9 @@ int speedyBatchWriteDevice(speedyBatch b, const int16_t* d_in, int64_t stride_fr
   memcpy(k1.factors, b->factors, sizeof(k1.factors));
   k1.tap_spec = b->d_tap_spec;
   k1.tap_stride = b->max_new_frames;
+  if (b->profiling) CU_TRY(cudaEventRecord(b->ev[0], st));
   CU_TRY(launch_k1(k1, st));  // streams with nonlinear factor 0 skip themselves
+  if (b->profiling) CU_TRY(cudaEventRecord(b->ev[1], st));
 
   K2Params k2;
   memset(&k2, 0, sizeof(k2));
@@ -531,6 +545,7 @@ int speedyBatchWriteDevice(speedyBatch b, const int16_t* d_in, int64_t stride_fr
   k2.counts = d_counts;
   k2.frames = frames;
   k2.feat = b->d_feat;
+  k2.feat_stride = b->max_new_frames;
   k2.max_new_frames = b->max_new_frames;
   k2.speeds = b->d_speeds;
   k2.speeds_stride = b->speeds_stride;
@@ -541,6 +556,7 @@ int speedyBatchWriteDevice(speedyBatch b, const int16_t* d_in, int64_t stride_fr
   k2.tap_speed = b->d_tap_speed;
   k2.tap_energy = b->d_tap_energy;
   CU_TRY(launch_k2(k2, st));
+  if (b->profiling) CU_TRY(cudaEventRecord(b->ev[2], st));
 
   K4Params k4;
   memset(&k4, 0, sizeof(k4));
@@ -560,6 +576,7 @@ int speedyBatchWriteDevice(speedyBatch b, const int16_t* d_in, int64_t stride_fr
   k4.out_capacity = b->out_capacity;
   k4.threads_per_stream = b->cfg.threads_per_stream;
   CU_TRY(launch_k4(k4, st));
+  if (b->profiling) CU_TRY(cudaEventRecord(b->ev[3], st));
 
   TailParams tp;
   memset(&tp, 0, sizeof(tp));
@@ -574,6 +591,10 @@ int speedyBatchWriteDevice(speedyBatch b, const int16_t* d_in, int64_t stride_fr
   tp.counts = d_counts;
   tp.frames = frames;
   CU_TRY(launch_tail(tp, st));
+  if (b->profiling) {
+    CU_TRY(cudaEventRecord(b->ev[4], st));
+    b->ev_recorded |= 1;
+  }
   b->hist_cur ^= 1;
   b->last_frames = frames;
   b->last_d_counts = d_counts;
@@ -598,7 +619,12 @@ int speedyBatchFlushDevice(speedyBatch b, void* cuda_stream) {
   k4.out = b->d_out;
   k4.out_capacity = b->out_capacity;
   k4.threads_per_stream = b->cfg.threads_per_stream;
+  if (b->profiling) CU_TRY(cudaEventRecord(b->ev[4], st));
   CU_TRY(launch_k4(k4, st));
+  if (b->profiling) {
+    CU_TRY(cudaEventRecord(b->ev[5], st));
+    b->ev_recorded |= 2;
+  }
   return 1;
 }
 
@@ -703,12 +729,119 @@ int speedyBatchRead(speedyBatch b, int16_t* h_out, int64_t stride_frames, int32_
   return 1;
 }
 
+int speedyBatchSetProfiling(speedyBatch b, int on) {
+  if (!b) return 0;
+  CU_TRY(cudaSetDevice(b->cfg.device));
+  if (on) {
+    for (int i = 0; i < 6; i++) {
+      if (!b->ev[i]) CU_TRY(cudaEventCreate(&b->ev[i]));
+    }
+  }
+  b->profiling = on ? 1 : 0;
+  b->ev_recorded = 0;
+  return 1;
+}
+
+// Device time of the kernels of the last write (and flush): spectral, tension,
+// sonic, tail, flush-sonic, in milliseconds (CUDA events on the launching stream).
+int speedyBatchGetKernelTimes(speedyBatch b, float* ms5) {
+  if (!b || !ms5 || !b->profiling) return 0;
+  CU_TRY(cudaSetDevice(b->cfg.device));
+  for (int i = 0; i < 5; i++) ms5[i] = 0.0f;
+  if (b->ev_recorded & 1) {
+    CU_TRY(cudaEventSynchronize(b->ev[4]));
+    for (int i = 0; i < 4; i++) CU_TRY(cudaEventElapsedTime(&ms5[i], b->ev[i], b->ev[i + 1]));
+  }
+  if (b->ev_recorded & 2) {
+    CU_TRY(cudaEventSynchronize(b->ev[5]));
+    CU_TRY(cudaEventElapsedTime(&ms5[4], b->ev[4], b->ev[5]));
+  }
+  return 1;
+}
+
+// One-shot over host buffers.  The streams are cut into slabs, each a child
+// batch with its own CUDA stream, so that the host->device copy of slab i+1 and
+// the device->host copy of slab i-1 overlap the kernels of slab i (streams are
+// independent: no cross-slab dependency exists).
 int speedyBatchProcess(speedyBatch b, const int16_t* h_in, int64_t frames, int16_t* h_out,
                        int64_t out_stride_frames, int32_t* h_out_counts) {
-  if (!b) return 0;
-  if (!speedyBatchReset(b, b->own_stream)) return 0;
-  return speedyBatchWrite(b, h_in, frames, frames, nullptr) && speedyBatchFlush(b) &&
-         speedyBatchRead(b, h_out, out_stride_frames, h_out_counts);
+  if (!b || !h_in || !h_out || frames < 1) return 0;
+  if (frames > b->cfg.max_write_frames) {
+    set_error("speedyBatchProcess: frames exceeds max_write_frames");
+    return 0;
+  }
+  CU_TRY(cudaSetDevice(b->cfg.device));
+  const int n = b->n, C = b->g.channels;
+  int n_slabs = n >= 64 ? 8 : (n >= 8 ? 4 : 1);
+  if (const char* e = getenv("SPEEDY_B200_SLABS")) n_slabs = atoi(e) > 0 ? atoi(e) : n_slabs;
+  if (n_slabs > n) n_slabs = n;
+  const int per = (n + n_slabs - 1) / n_slabs;
+  if (b->slabs.empty() || b->slab_frames < frames || (int)b->slabs.size() != n_slabs) {
+    for (speedyBatch c : b->slabs) speedyBatchDestroy(c);
+    b->slabs.clear();
+    for (int i = 0; i < n_slabs; i++) {
+      speedyBatchConfig cfg = b->cfg;
+      cfg.num_streams = std::min(per, n - i * per);
+      cfg.max_write_frames = frames;
+      cfg.taps = 0;
+      speedyBatch c = speedyBatchCreate(&cfg);
+      if (!c) return 0;
+      b->slabs.push_back(c);
+      if (!ensure_stage(c, frames)) return 0;
+    }
+    b->slab_frames = frames;
+  }
+  const size_t in_row = (size_t)frames * C * sizeof(int16_t);
+  std::vector<cudaEvent_t> done(n_slabs);
+  for (int i = 0; i < n_slabs; i++) {
+    speedyBatch c = b->slabs[i];
+    const int s0 = i * per;
+    cudaStream_t st = c->own_stream;
+    if (!reset_state(c, st)) return 0;
+    // per-stream parameters follow the parent's
+    CU_TRY(cudaMemcpyAsync(c->st.speed, b->st.speed + s0, sizeof(float) * c->n, cudaMemcpyDeviceToDevice, st));
+    CU_TRY(cudaMemcpyAsync(c->st.sonic_speed, b->st.speed + s0, sizeof(float) * c->n, cudaMemcpyDeviceToDevice, st));
+    CU_TRY(cudaMemcpyAsync(c->st.nonlinear, b->st.nonlinear + s0, sizeof(float) * c->n, cudaMemcpyDeviceToDevice, st));
+    CU_TRY(cudaMemcpyAsync(c->st.feedback, b->st.feedback + s0, sizeof(float) * c->n, cudaMemcpyDeviceToDevice, st));
+    CU_TRY(cudaMemcpy2DAsync(c->d_stage, in_row, h_in + (size_t)s0 * frames * C, in_row, in_row, c->n,
+                             cudaMemcpyHostToDevice, st));
+    if (!speedyBatchWriteDevice(c, c->d_stage, frames, frames, nullptr, st)) return 0;
+    if (!speedyBatchFlushDevice(c, st)) return 0;
+    CU_TRY(cudaMemcpyAsync(c->h_pinned_counts, c->st.out_count, sizeof(int32_t) * c->n, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+    CU_TRY(cudaEventRecord(done[i], st));
+  }
+  int ok = 1;
+  for (int i = 0; i < n_slabs; i++) {
+    speedyBatch c = b->slabs[i];
+    const int s0 = i * per;
+    cudaStream_t st = c->own_stream;
+    if (cudaEventSynchronize(done[i]) != cudaSuccess) ok = 0;
+    cudaEventDestroy(done[i]);
+    if (!ok) continue;
+    long long mx = 0;
+    for (int s = 0; s < c->n; s++) {
+      long long cnt = c->h_pinned_counts[s];
+      if (cnt > out_stride_frames) cnt = out_stride_frames;
+      if (h_out_counts) h_out_counts[s0 + s] = (int32_t)cnt;
+      if (cnt > mx) mx = cnt;
+    }
+    if (mx > 0) {
+      const size_t row = (size_t)mx * C * sizeof(int16_t);
+      if (cudaMemcpy2DAsync(h_out + (size_t)s0 * out_stride_frames * C, (size_t)out_stride_frames * C * sizeof(int16_t),
+                            c->d_out, (size_t)c->out_capacity * C * sizeof(int16_t), row, c->n,
+                            cudaMemcpyDeviceToHost, st) != cudaSuccess)
+        ok = 0;
+    }
+    read_finish_kernel<<<(c->n + 127) / 128, 128, 0, st>>>(c->n, c->st.out_count, c->st.status, c->d_counts_stage,
+                                                           out_stride_frames);
+    count_launch();
+  }
+  for (int i = 0; i < n_slabs; i++) {
+    if (cudaStreamSynchronize(b->slabs[i]->own_stream) != cudaSuccess) ok = 0;
+  }
+  if (!ok) set_error(std::string("speedyBatchProcess: ") + cudaGetErrorString(cudaGetLastError()));
+  return ok;
 }
 
 int speedyBatchGetStatus(speedyBatch b, int32_t* status) {

@@ -61,6 +61,89 @@ struct Source {
   }
 };
 
+// Stage `count` mono samples (channel average, soniclib.c:271-274) of frames
+// [start, start + count) into shared memory, dst[i] = frame start + i.  Frames
+// outside [src.hist_base, lim) read as 0.  The bulk comes from the caller's buffer
+// with 16-byte loads (8 int16 per load, several in flight per thread); only the
+// pieces in the carried history, or a misaligned head/tail, go one sample at a
+// time.  raw16 (optional, channels > 1) receives the interleaved samples too.
+template <int THREADS, typename T>
+__device__ __forceinline__ void stage_mono(const Source& src, long long start, int count, long long lim,
+                                           T* dst, short* raw16, int tid) {
+  const int C = src.channels;
+  if (lim > src.t_new) lim = src.t_new;
+  // frames served by the vector path: [v0, v1), inside the caller's buffer
+  long long v0 = start > src.t_old ? start : src.t_old;
+  long long v1 = start + count < lim ? start + count : lim;
+  const bool vec_ok = src.in != nullptr && (C == 1 || C == 2) && v1 - v0 >= 64 &&
+                      ((reinterpret_cast<size_t>(src.in) & (C == 2 ? 3 : 1)) == 0);
+  if (vec_ok) {
+    // align v0 up / v1 down to 16-byte boundaries of the caller's buffer
+    const int fpv = 8 / C;  // frames per 16-byte vector
+    const long long a0 = (long long)((reinterpret_cast<size_t>(src.in) >> 1) & 7) / C;  // frame offset of base
+    const long long g0 = v0 - src.t_old + a0, g1 = v1 - src.t_old + a0;
+    const long long c0 = (g0 + fpv - 1) / fpv, c1 = g1 / fpv;
+    if (c1 > c0) {
+      const long long fv0 = src.t_old + c0 * fpv - a0;  // first frame of vector c0
+      const int4* vp = reinterpret_cast<const int4*>(src.in + (fv0 - src.t_old) * C);
+      const int nvec = (int)(c1 - c0);
+      T* d = dst + (fv0 - start);
+      short* r = raw16 ? raw16 + (fv0 - start) * C : nullptr;
+#pragma unroll 4
+      for (int v = tid; v < nvec; v += THREADS) {
+        const int4 q = vp[v];
+        const int w[4] = {q.x, q.y, q.z, q.w};
+        if (C == 1) {
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            d[v * 8 + 2 * j] = (T)(short)(w[j] & 0xffff);
+            d[v * 8 + 2 * j + 1] = (T)(short)(w[j] >> 16);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const int l = (short)(w[j] & 0xffff), h = (short)(w[j] >> 16);
+            d[v * 4 + j] = (T)((l + h) / 2);
+            if (r) {
+              r[(v * 4 + j) * 2] = (short)l;
+              r[(v * 4 + j) * 2 + 1] = (short)h;
+            }
+          }
+        }
+      }
+      v0 = fv0;
+      v1 = fv0 + (long long)nvec * fpv;
+    } else {
+      v1 = v0;
+    }
+  } else {
+    v1 = v0;
+  }
+  // everything else: [start, v0) and [v1, start + count)
+  const long long end = start + count;
+  const int n_head = (int)(v0 - start), n_tail = (int)(end - v1);
+  for (int i = tid; i < n_head + n_tail; i += THREADS) {
+    const long long f = i < n_head ? start + i : v1 + (i - n_head);
+    int m = 0;
+    if (f >= src.hist_base && f < lim) {
+      if (C == 1) {
+        m = src.raw(f, 0);
+      } else {
+        int sum = 0;
+        for (int c = 0; c < C; c++) {
+          const int x = src.raw(f, c);
+          sum += x;
+          if (raw16) raw16[(f - start) * C + c] = (short)x;
+        }
+        m = sum / C;
+      }
+    } else if (raw16 && C > 1) {
+      for (int c = 0; c < C; c++) raw16[(f - start) * C + c] = 0;
+    }
+    dst[f - start] = (T)m;
+  }
+}
+
 // Per-stream device state, structure of arrays (index = stream).
 struct StreamState {
   // totals
@@ -75,10 +158,9 @@ struct StreamState {
   float* lp_diff;
   float* cur_dur;
   float* des_dur;
-  float* ring_comp;       // [kRing][n] compressed energy by at_time & 31
-  float* ring_energy;     // [kRing][n] frame energy
-  float* ring_lsd;        // [kRing][n] raw local spectral difference
-  float* ring_lp;         // [kRing][n] energy low-pass (features tap)
+  float* ring_comp;       // [n][kRing] compressed energy by at_time & 31
+  float* ring_energy;     // [n][kRing] frame energy
+  float* ring_lsd;        // [n][kRing] raw local spectral difference
   // Sonic state
   long long* sonic_head;  // absolute frame of the FIFO head
   long long* sonic_fed;   // absolute frame one past the FIFO tail

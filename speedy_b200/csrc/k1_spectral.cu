@@ -131,22 +131,20 @@ __device__ __forceinline__ float inverse_norm(float energy) {
   return (float)(1.0 / (sqrt((double)energy) + (double)eps));
 }
 
-// speedy.c:705-719 for `half` bins held in shared memory (bin 0 skipped).
-// cur/last: magnitudes of at_time a and a-1; e_cur/e_last their energies; mx the
-// largest magnitude of cur over bins 1..half-1.
-__device__ __forceinline__ float spectral_difference(const float* cur, const float* last, int half,
-                                                     float e_cur, float e_last, float mx, int lane) {
-  const float eps = 2.2204e-16f;
-  const float inv_c = inverse_norm(e_cur);
-  const float inv_l = inverse_norm(e_last);
-  const float thr = (float)((double)mx / 100.0);
+// speedy.c:705-719 in the log domain.  The reference sums, over the bins where both
+// spectra exceed max(cur)/100, |log((cur_i*inv_c + eps) / (last_i*inv_l + eps))|.
+// For those bins eps = 2.2e-16 is below half an ulp of the normalised value (which
+// is at least 0.01/sqrt(N/2)), so the term equals |log cur_i - log last_i +
+// (log inv_c - log inv_l)|; the logarithm of every magnitude is taken once, when
+// the magnitude is produced, instead of once per frame pair.
+//   lc/ll: log magnitudes of at_time a and a-1 (bin 0 unused); log_thr = log of
+//   max(cur)/100; dl = log inv_c - log inv_l.
+__device__ __forceinline__ float spectral_difference_log(const float* lc, const float* ll, int half,
+                                                         float log_thr, float dl, int lane) {
   float acc = 0.0f;
   for (int i = 1 + lane; i < half; i += 32) {
-    float c = cur[i], l = last[i];
-    if (c > thr && l > thr) {
-      float ratio = __fdiv_rn(__fadd_rn(__fmul_rn(c, inv_c), eps), __fadd_rn(__fmul_rn(l, inv_l), eps));
-      acc += fabsf(logf(ratio));
-    }
+    const float c = lc[i], l = ll[i];
+    if (c > log_thr && l > log_thr) acc += fabsf((c - l) + dl);
   }
   return warp_sum(acc);
 }
@@ -160,10 +158,12 @@ constexpr int P16 = 80;             // window - step
 constexpr int H16 = 240;            // N/2 bins kept
 constexpr int kRun = K1_RUN;        // new windows per warp (plus one halo)
 constexpr int kSampN = (kRun + 1) * S16 + P16;
+constexpr float kPreHi = 0.97f;                          // speedy.c:422
+constexpr float kPreLo = (float)(0.97 - (double)0.97f);  // remainder of the double constant
 
 struct WarpSmem480 {
   float2 z[2][240];      // per slot: windowed input (aliased), then transposes
-  float mag[3][240];     // previous, slot A, slot B
+  float lmag[3][240];    // log |X| of the previous window, slot A, slot B
   short samp[kSampN + 8];
 };
 
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(WARPS * 32) k1_spectral_480(K1Params p) {
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < 240; i += WARPS * 32) {
-    s_win[i] = p.window[i];
+    s_win[i] = p.window[i] * 3.0517578125e-05f;  // Hamming / 32768: exact scaling
     s_tw480[i] = p.tw_n[i];  // W_480^k
   }
   __syncthreads();
@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(WARPS * 32) k1_spectral_480(K1Params p) {
   // Stage the run's samples (mono down-mix) once: windows k0-1 .. k1-1.
   const long long base = (long long)(k0 - 1) * S16;
   const int need = (k1 - k0 + 1) * S16 + P16;
-  for (int i = lane; i < need; i += 32) ws.samp[i] = (short)src.mono(base + i);
+  stage_mono<32, short>(src, base, need, t_new, ws.samp, nullptr, lane);
   __syncwarp();
 
   // Per-lane constants.
@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(WARPS * 32) k1_spectral_480(K1Params p) {
   const int slot2 = lane >> 4, q2 = (lane >> 3) & 1, j1_2 = lane & 7;
 
   int ip = 0, ia = 1, ib = 2;  // rotating indices into ws.mag
-  float e_prev = 0.0f;
+  float linv_prev = 0.0f;
 
   // windows are processed in pairs (kk, kk+1), starting at the halo k0-1
   for (int kk = k0 - 1; kk < k1; kk += 2) {
@@ -241,11 +241,12 @@ __global__ void __launch_bounds__(WARPS * 32) k1_spectral_480(K1Params p) {
           // state entering sample 0 is the last sample of the previous window,
           // i.e. sample P-1 of this one (speedy.c:416-425; window k-1 ends at
           // k*S + P - 1); 0 before the first window.
-          int xp = (n > 0) ? ws.samp[o + n - 1] : (k >= 1 ? ws.samp[o + P16 - 1] : 0);
-          int xc = ws.samp[o + n];
-          double fc = (double)((float)xc * 3.0517578125e-05f);
-          double fp = (double)((float)xp * 3.0517578125e-05f);
-          float y = (float)__dsub_rn(fc, __dmul_rn(0.97, fp));
+          const float xp = (float)((n > 0) ? ws.samp[o + n - 1] : (k >= 1 ? ws.samp[o + P16 - 1] : 0));
+          const float xc = (float)ws.samp[o + n];
+          // y = x - 0.97 * state (speedy.c:422, evaluated there in double): 0.97 is
+          // split into a float and its remainder so the constant carries no error;
+          // the /32768 of speedy.c:558 is folded into the window table.
+          const float y = __fmaf_rn(-kPreLo, xp, __fmaf_rn(-kPreHi, xp, xc));
           out = __fmul_rn(y, s_win[n]);
         }
         v[n] = out;
@@ -304,8 +305,11 @@ __global__ void __launch_bounds__(WARPS * 32) k1_spectral_480(K1Params p) {
     float e_slot[2], mx_slot[2];
 #pragma unroll
     for (int slot = 0; slot < 2; slot++) {
+      const int k = kk + slot;
       const float2* Z = ws.z[slot];
-      float* mag = ws.mag[slot == 0 ? ia : ib];
+      float* lmag = ws.lmag[slot == 0 ? ia : ib];
+      float* tap = nullptr;
+      if (p.tap_spec && k >= k0 && k < k1) tap = p.tap_spec + ((size_t)s * p.tap_stride + (k - kA)) * 480;
       float e = 0.0f, mx = 0.0f;
       for (int kb = lane; kb < H16; kb += 32) {
         float2 zk = Z[kb];
@@ -317,10 +321,15 @@ __global__ void __launch_bounds__(WARPS * 32) k1_spectral_480(K1Params p) {
         float re = sum.x + wd.x, im = sum.y + wd.y;
         // speedy.c:434-436: sqrt(r*r + i*i), products and sum rounded to float
         float m = __fsqrt_rn(__fadd_rn(__fmul_rn(re, re), __fmul_rn(im, im)));
-        mag[kb] = m;
+        lmag[kb] = logf(m);
         if (kb >= 1) {
           e += m * m;
           mx = fmaxf(mx, m);
+        }
+        if (tap) {
+          tap[kb] = m;
+          if (kb >= 1) tap[480 - kb] = m;
+          if (kb == 0) tap[240] = fabsf(zk.x - zk.y);  // X[N/2] = Re(Z0) - Im(Z0)
         }
       }
       e_slot[slot] = warp_sum(e);
@@ -329,30 +338,22 @@ __global__ void __launch_bounds__(WARPS * 32) k1_spectral_480(K1Params p) {
     __syncwarp();
 
     // ---- spectral difference against the previous window, outputs ---------
+    float linv_slot[2];
 #pragma unroll
     for (int slot = 0; slot < 2; slot++) {
       const int k = kk + slot;
-      const float* cur = ws.mag[slot == 0 ? ia : ib];
-      const float* last = ws.mag[slot == 0 ? ip : ia];
-      const float e_last = slot == 0 ? e_prev : e_slot[0];
+      linv_slot[slot] = logf(inverse_norm(e_slot[slot]));
+      const float* lc = ws.lmag[slot == 0 ? ia : ib];
+      const float* ll = ws.lmag[slot == 0 ? ip : ia];
+      const float linv_last = slot == 0 ? linv_prev : linv_slot[0];
       if (k >= k0 && k < k1) {
-        float lsd = spectral_difference(cur, last, H16, e_slot[slot], e_last, mx_slot[slot], lane);
+        const float log_thr = logf((float)((double)mx_slot[slot] / 100.0));  // speedy.c:709
+        float lsd = spectral_difference_log(lc, ll, H16, log_thr, linv_slot[slot] - linv_last, lane);
         const int j = k - kA;
-        if (lane == 0) p.feat[(size_t)j * p.n_streams + s] = make_float2(e_slot[slot], lsd);
-        if (p.tap_spec) {
-          float* row = p.tap_spec + ((size_t)s * p.tap_stride + j) * 480;
-          for (int i = lane; i < 240; i += 32) {
-            row[i] = cur[i];
-            if (i >= 1) row[480 - i] = cur[i];
-          }
-          if (lane == 0) {
-            float2 z0 = ws.z[slot][0];  // X[N/2] = Re(Z0) - Im(Z0)
-            row[240] = fabsf(z0.x - z0.y);
-          }
-        }
+        if (lane == 0) p.feat[(size_t)s * p.feat_stride + j] = make_float2(e_slot[slot], lsd);
       }
     }
-    e_prev = e_slot[1];
+    linv_prev = linv_slot[1];
     // rotate: slot B becomes "previous"
     int t = ip; ip = ib; ib = ia; ia = t;
     __syncwarp();
@@ -487,7 +488,7 @@ __global__ void __launch_bounds__(THREADS) k1_spectral_generic(K1Params p) {
       }
       __syncthreads();
       const int j = k - kA;
-      if (tid == 0) p.feat[(size_t)j * p.n_streams + s] = make_float2(e_cur, s_lsd);
+      if (tid == 0) p.feat[(size_t)s * p.feat_stride + j] = make_float2(e_cur, s_lsd);
       if (p.tap_spec) {
         float* row = p.tap_spec + ((size_t)s * p.tap_stride + j) * N;
         for (int i = tid; i < N; i += THREADS) {

@@ -25,8 +25,9 @@ struct K1Params {
   long long in_stride_frames;
   const int32_t* counts;         // optional per-stream frame counts
   long long frames;              // uniform frame count
-  // per-call scratch out: [max_new_frames][n] (energy, raw spectral difference)
+  // per-call scratch out: [n][feat_stride] (energy, raw spectral difference)
   float2* feat;
+  int feat_stride;
   int max_new_frames;
   int runs_per_stream;           // filled by the launcher
   // tables
@@ -48,7 +49,8 @@ struct K2Params {
   int n_streams;
   const int32_t* counts;
   long long frames;
-  const float2* feat;            // from K1
+  const float2* feat;            // from K1, [n][feat_stride]
+  int feat_stride;
   int max_new_frames;
   float* speeds;                 // out: [n][speeds_stride]
   int speeds_stride;
