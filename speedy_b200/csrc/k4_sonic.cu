@@ -1,5 +1,5 @@
 // K4 — Sonic time-scale modification: AMDF pitch-period search and
-// pitch-synchronous overlap-add, one CTA per stream.
+// pitch-synchronous overlap-add, one warp per stream.
 //
 // Replaces what the reference does through upstream Sonic
 // (soniclib.c:354, 369-370, 398, 547, 551 -> sonicIntSetSpeed,
@@ -13,12 +13,19 @@
 // float expressions that size a splice (period / (speed - 1) ...), which are
 // written with explicit IEEE _rn intrinsics (and the file is built with
 // --fmad=false) so they round exactly as the C code does.  Integer sums are
-// associative, so splitting the AMDF sums across threads cannot change a result:
+// associative, so splitting the AMDF sums across lanes cannot change a result:
 // given identical per-frame speeds the output is bit-exact.
+//
+// Why one warp per stream.  The splice cursor is strictly sequential (the next
+// position depends on the period just found), so a stream is a chain of ~80 pitch
+// iterations per second of audio; parallelism comes from the streams.  A warp
+// needs no block barrier, no cross-warp reduction and executes the uniform
+// bookkeeping once instead of once per warp; the profile of the earlier
+// multi-warp version was dominated by exactly that overhead.
 //
 // Sonic's input FIFO is never materialised: the stream keeps two absolute
 // cursors (head = first unconsumed frame, fed = one past the last frame handed
-// to Sonic) and the CTA slides a shared-memory window over the caller's buffer.
+// to Sonic) and the warp slides a shared-memory window over the caller's buffer.
 // The output cursor is the per-stream pending count in the output buffer.
 //
 // AMDF layout.  The window is kept in shared memory as 32-bit mono samples, so
@@ -26,10 +33,8 @@
 // instruction).  Lags are processed in groups of four consecutive lags starting
 // at a multiple of four: for an aligned block of four samples a[blk..blk+3] the
 // operands of lags 4k..4k+3 are the seven values b[blk+4k .. blk+4k+6], i.e. two
-// more aligned LDS.128.  3 loads + 16 VABSDIFF per 16 differences.  The few
-// samples before the first / after the last aligned block of each lag (at most
-// nine) are summed by one thread per lag, which also initialises the per-lag
-// accumulator the block sums are added to.
+// more aligned LDS.128: 3 loads + 16 VABSDIFF per 16 differences.  The first and
+// last block of a lag group are the same code under a per-element mask.
 #include <stdlib.h>
 
 #include "kernels.cuh"
@@ -38,40 +43,44 @@ namespace speedy {
 
 namespace {
 
-template <int THREADS>
-struct Sonic {
-  static constexpr int NW = THREADS / 32;
+constexpr int kPad = 16;  // over-read slack behind the window and the decimated copy
+constexpr unsigned kFull = 0xffffffffu;
 
+struct Sonic {
   // geometry
   int C, S, minP, maxP, maxReq, skip;
   long long cap;
-  // shared memory
-  int* w32;        // mono window, 32-bit [bufN + 8]
-  short* buf;      // interleaved raw window (C > 1 only) [bufN * C]
-  int* ds32;       // decimated mono [maxReq / skip + 8]
-  unsigned* acc;   // per-lag AMDF sums
-  unsigned long long* red;  // [2 * NW]
+  // shared memory (this warp's slice)
+  int* w32;                 // mono window, 32-bit [bufN + kPad]
+  short* buf;               // interleaved raw window (C > 1 only) [bufN * C]
+  int* ds32;                // decimated mono [maxReq / skip + kPad]
+  unsigned* acc;            // per-lag AMDF sums
+  unsigned short* items;    // coarse pass: work item -> (group << 8 | block)
+  int n_items;
   int bufN;
-  // window state (uniform across the CTA)
+  // window state (warp-uniform)
   long long bufStart;
   int bufLen;
   // source
   Source src;
   long long zero_from;  // frames >= this read as silence (flush padding)
-  // stream state (uniform)
+  // stream state (warp-uniform)
   long long head, fed, outTotal;
   int prevPeriod, prevMinDiff, remCopy, outCount, status;
   short* out;
-  int tid;
+  int lane;
+  // fine-pass lane mapping: G sub-lanes per lag group
+  int fG, fPerRound, fGi0, fg;
+  unsigned dec_magic;
 
   // Make [start, start + count) resident in the shared window (count <= bufN - 8).
-  __device__ void ensure(long long start, int count) {
+  __device__ __forceinline__ void ensure(long long start, int count) {
     if (start >= bufStart && start + count <= bufStart + bufLen) return;
-    __syncthreads();  // everyone is done with the old window
+    __syncwarp();  // every lane is done with the old window
     bufStart = start & ~7LL;  // keeps the 16-byte loads of the refill aligned
     bufLen = bufN;
-    stage_mono<THREADS, int>(src, bufStart, bufN, zero_from, w32, C > 1 ? buf : nullptr, tid);
-    __syncthreads();
+    stage_mono<32, int>(src, bufStart, bufN, zero_from, w32, C > 1 ? buf : nullptr, lane);
+    __syncwarp();
   }
 
   __device__ __forceinline__ void advance_out(int n) {
@@ -85,19 +94,19 @@ struct Sonic {
   }
 
   // Append n frames starting at absolute frame `from` to the output.
-  __device__ void emit_copy(long long from, int n, int out_offset_frames) {
+  __device__ __forceinline__ void emit_copy(long long from, int n, int out_offset_frames) {
     const int o0 = (int)(from - bufStart);
     const int total = n * C;
     const long long base = (long long)(outCount + out_offset_frames) * C;
     const long long room = cap * C - base;
     short* o = out + base;
     if (C == 1) {
-      for (int i = tid; i < total; i += THREADS) {
+      for (int i = lane; i < total; i += 32) {
         if (i < room) o[i] = (short)w32[o0 + i];
       }
     } else {
       const short* p = buf + (size_t)o0 * C;
-      for (int i = tid; i < total; i += THREADS) {
+      for (int i = lane; i < total; i += 32) {
         if (i < room) o[i] = p[i];
       }
     }
@@ -105,21 +114,21 @@ struct Sonic {
 
   // out[t] = (down[t]*(n-t) + up[t]*t) / n per channel, C integer arithmetic.
   // down/up are absolute frames inside the window.
-  __device__ void overlap_add(int n, long long down, long long up, int out_offset_frames) {
+  __device__ __forceinline__ void overlap_add(int n, long long down, long long up, int out_offset_frames) {
     const int d0 = (int)(down - bufStart), u0 = (int)(up - bufStart);
     const int total = n * C;
     const long long base = (long long)(outCount + out_offset_frames) * C;
     const long long room = cap * C - base;
     short* o = out + base;
     if (C == 1) {
-      for (int t = tid; t < total; t += THREADS) {
+      for (int t = lane; t < total; t += 32) {
         int v = (w32[d0 + t] * (n - t) + w32[u0 + t] * t) / n;
         if (t < room) o[t] = (short)v;
       }
     } else {
       const short* dp = buf + (size_t)d0 * C;
       const short* up_ = buf + (size_t)u0 * C;
-      for (int i = tid; i < total; i += THREADS) {
+      for (int i = lane; i < total; i += 32) {
         int t = i / C;
         int v = ((int)dp[i] * (n - t) + (int)up_[i] * t) / n;
         if (i < room) o[i] = (short)v;
@@ -130,11 +139,10 @@ struct Sonic {
   // Upstream downSampleInput: sum `skip` frames x C channels, C integer division
   // (truncating).  |sum| < 2^21 and the divisor is small, so the quotient is exact
   // as (|sum| * ceil(2^32 / divisor)) >> 32.
-  __device__ void decimate(int off) {
+  __device__ __forceinline__ void decimate(int off) {
     const int count = maxReq / skip;
     const int per = C * skip;
-    const unsigned magic = (unsigned)((0x100000000ULL + per - 1) / per);
-    for (int i = tid; i < count; i += THREADS) {
+    for (int i = lane; i < count; i += 32) {
       int v = 0;
       if (C == 1) {
         const int* q = w32 + off + i * skip;
@@ -143,125 +151,134 @@ struct Sonic {
         const short* q = buf + ((size_t)off + (size_t)i * skip) * C;
         for (int j = 0; j < per; j++) v += q[j];
       }
-      const int qa = (int)__umulhi((unsigned)abs(v), magic);
+      const int qa = (int)__umulhi((unsigned)abs(v), dec_magic);
       ds32[i] = v < 0 ? -qa : qa;
     }
-    __syncthreads();
+    __syncwarp();
   }
 
-  // Thread mapping of the aligned-block pass for up to `max_groups` lag groups:
-  // G sub-lanes per group, fixed per search stage so that no thread divides.
-  struct Map {
-    int G, per_round, gi0, g;
-    __device__ void init(int max_groups, int tid) {
-      G = THREADS / max_groups;
-      if (G < 1) G = 1;
-      per_round = THREADS / G;
-      gi0 = tid / G;
-      g = tid - gi0 * G;
-      if (tid >= per_round * G) gi0 = 1 << 30;  // idle thread
+  // |a - b| sums of one aligned block of four samples for the four lags
+  // pg .. pg+3 (pg a multiple of four).  Sample x = blk + m contributes to lag
+  // pg + l iff off <= x < off + pg + l.
+  __device__ __forceinline__ void block_sads(const int* arr, int blk, int pg, int off, unsigned (&d)[4]) {
+    const int4 av = *reinterpret_cast<const int4*>(arr + blk);
+    const int4 b0 = *reinterpret_cast<const int4*>(arr + blk + pg);
+    const int4 b1 = *reinterpret_cast<const int4*>(arr + blk + pg + 4);
+    if (blk >= off && blk + 3 < off + pg) {
+      d[0] = __sad(av.x, b0.x, d[0]); d[0] = __sad(av.y, b0.y, d[0]);
+      d[0] = __sad(av.z, b0.z, d[0]); d[0] = __sad(av.w, b0.w, d[0]);
+      d[1] = __sad(av.x, b0.y, d[1]); d[1] = __sad(av.y, b0.z, d[1]);
+      d[1] = __sad(av.z, b0.w, d[1]); d[1] = __sad(av.w, b1.x, d[1]);
+      d[2] = __sad(av.x, b0.z, d[2]); d[2] = __sad(av.y, b0.w, d[2]);
+      d[2] = __sad(av.z, b1.x, d[2]); d[2] = __sad(av.w, b1.y, d[2]);
+      d[3] = __sad(av.x, b0.w, d[3]); d[3] = __sad(av.y, b1.x, d[3]);
+      d[3] = __sad(av.z, b1.y, d[3]); d[3] = __sad(av.w, b1.z, d[3]);
+    } else {
+      const int a[4] = {av.x, av.y, av.z, av.w};
+      const int b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      const int first = off - blk;      // m >= first
+      const int last = off + pg - blk;  // m < last + l
+#pragma unroll
+      for (int l = 0; l < 4; l++) {
+#pragma unroll
+        for (int m = 0; m < 4; m++) {
+          if (m >= first && m < last + l) d[l] = __sad(a[m], b[m + l], d[l]);
+        }
+      }
     }
-  };
-  Map map_coarse, map_fine;
+  }
+
+  // Exact arg-min / arg-max of diff/period over the warp's candidates (one per
+  // lane, period 0 = none).  The C scan compares by cross-multiplication with
+  // strict inequalities, so ties go to the smaller lag.  A float quotient picks
+  // the lanes within 2e-6 of the extremum (a superset of the true extremum, its
+  // relative error is below 4e-7); almost always that is one lane, otherwise the
+  // short list is resolved exactly.
+  template <bool kMin>
+  __device__ __forceinline__ void pick(unsigned diff, int period, unsigned* out_diff, int* out_period) {
+    const float f = period ? __fdividef((float)diff, (float)period) : (kMin ? 3.0e38f : 0.0f);
+    const unsigned key = __float_as_uint(f);
+    const float ext = __uint_as_float(kMin ? __reduce_min_sync(kFull, key) : __reduce_max_sync(kFull, key));
+    const bool near = period != 0 && (kMin ? f <= ext * 1.000002f : f >= ext * 0.999998f);
+    unsigned ballot = __ballot_sync(kFull, near);
+    int src_lane = __ffs(ballot) - 1;
+    unsigned bd = __shfl_sync(kFull, diff, src_lane);
+    int bp = __shfl_sync(kFull, period, src_lane);
+    ballot &= ballot - 1;
+    while (ballot) {  // rare: several candidates within rounding of each other
+      src_lane = __ffs(ballot) - 1;
+      ballot &= ballot - 1;
+      const unsigned cd = __shfl_sync(kFull, diff, src_lane);
+      const int cp = __shfl_sync(kFull, period, src_lane);
+      const unsigned long long l = (unsigned long long)cd * (unsigned)bp;
+      const unsigned long long r = (unsigned long long)bd * (unsigned)cp;
+      const bool better = kMin ? (l < r || (l == r && cp < bp)) : (l > r || (l == r && cp < bp));
+      if (better) {
+        bd = cd;
+        bp = cp;
+      }
+    }
+    *out_diff = bd;
+    *out_period = bp;
+  }
 
   // AMDF over lags lo..hi on a[i] = arr[off + i].  Returns the best lag; *minDiff /
   // *maxDiff are the per-sample differences at the best and worst lag.
-  __device__ __forceinline__ int search(const int* arr, int off, int lo, int hi, const Map& map,
-                                        int* minDiff, int* maxDiff) {
-    const int g0 = lo >> 2;                 // first lag group (lags 4*g0 .. 4*g0+3)
+  __device__ __forceinline__ int search(const int* arr, int off, int lo, int hi, bool coarse, int* minDiff,
+                                        int* maxDiff) {
+    const int g0 = lo >> 2;  // first lag group (lags 4*g0 .. 4*g0+3)
     const int ngroups = (hi >> 2) - g0 + 1;
     const int nlag = ngroups * 4;
-    const int A0 = (off + 3) & ~3;          // first aligned block inside the range
-    // ---- edge samples, one thread per lag; initialises acc[] -------------------
-    for (int li = tid; li < nlag; li += THREADS) {
-      const int p = 4 * g0 + li;
-      const int pg = p & ~3;
-      int A1 = (off + pg) & ~3;             // end of the group's aligned blocks
-      if (A1 < A0) A1 = A0;
-      unsigned d = 0;
-      if (p >= lo && p <= hi) {
-        const int* a = arr + off;
-        const int head_n = min(A0 - off, p);
-        for (int i = 0; i < head_n; i++) d = __sad(a[i], a[i + p], d);
-        for (int i = max(A1 - off, head_n); i < p; i++) d = __sad(a[i], a[i + p], d);
+    for (int li = lane; li < nlag; li += 32) acc[li] = 0;
+    __syncwarp();
+    if (coarse) {
+      // off == 0 and the lag range is fixed: a precomputed flat list of blocks
+      for (int w = lane; w < n_items; w += 32) {
+        const int it = items[w];
+        const int gi = it >> 8, j = it & 255;
+        unsigned d[4] = {0u, 0u, 0u, 0u};
+        block_sads(arr, 4 * j, 4 * (g0 + gi), 0, d);
+        atomicAdd(&acc[4 * gi + 0], d[0]);
+        atomicAdd(&acc[4 * gi + 1], d[1]);
+        atomicAdd(&acc[4 * gi + 2], d[2]);
+        atomicAdd(&acc[4 * gi + 3], d[3]);
       }
-      acc[li] = d;
-    }
-    __syncthreads();
-    // ---- aligned blocks: 4 lags x 4 samples per step ----------------------------
-    for (int gi = map.gi0; gi < ngroups; gi += map.per_round) {
-      const int pg = 4 * (g0 + gi);
-      const int A1 = (off + pg) & ~3;
-      const int nb = (A1 - A0) >> 2;
-      unsigned d0 = 0, d1 = 0, d2 = 0, d3 = 0;
-      for (int j = map.g; j < nb; j += map.G) {
-        const int blk = A0 + 4 * j;
-        const int4 av = *reinterpret_cast<const int4*>(arr + blk);
-        const int4 b0 = *reinterpret_cast<const int4*>(arr + blk + pg);
-        const int4 b1 = *reinterpret_cast<const int4*>(arr + blk + pg + 4);
-        d0 = __sad(av.x, b0.x, d0); d0 = __sad(av.y, b0.y, d0);
-        d0 = __sad(av.z, b0.z, d0); d0 = __sad(av.w, b0.w, d0);
-        d1 = __sad(av.x, b0.y, d1); d1 = __sad(av.y, b0.z, d1);
-        d1 = __sad(av.z, b0.w, d1); d1 = __sad(av.w, b1.x, d1);
-        d2 = __sad(av.x, b0.z, d2); d2 = __sad(av.y, b0.w, d2);
-        d2 = __sad(av.z, b1.x, d2); d2 = __sad(av.w, b1.y, d2);
-        d3 = __sad(av.x, b0.w, d3); d3 = __sad(av.y, b1.x, d3);
-        d3 = __sad(av.z, b1.y, d3); d3 = __sad(av.w, b1.z, d3);
-      }
-      if (map.g < nb) {
-        atomicAdd(&acc[4 * gi + 0], d0);
-        atomicAdd(&acc[4 * gi + 1], d1);
-        atomicAdd(&acc[4 * gi + 2], d2);
-        atomicAdd(&acc[4 * gi + 3], d3);
+    } else {
+      const int B0 = off & ~3;
+      for (int gi = fGi0; gi < ngroups; gi += fPerRound) {
+        const int pg = 4 * (g0 + gi);
+        const int nblk = ((((off + pg + 2) & ~3) + 4) - B0) >> 2;
+        unsigned d[4] = {0u, 0u, 0u, 0u};
+        for (int j = fg; j < nblk; j += fG) block_sads(arr, B0 + 4 * j, pg, off, d);
+        atomicAdd(&acc[4 * gi + 0], d[0]);
+        atomicAdd(&acc[4 * gi + 1], d[1]);
+        atomicAdd(&acc[4 * gi + 2], d[2]);
+        atomicAdd(&acc[4 * gi + 3], d[3]);
       }
     }
-    __syncthreads();
-    // ---- best / worst lag ---------------------------------------------------------
-    // The C scan keeps the lag with the smallest (largest) diff/period, comparing by
-    // cross-multiplication with strict inequalities, i.e. ties go to the smaller lag.
-    // key = floor(diff * 2^23 / period) orders the ratios exactly: two different
-    // ratios of integers with periods < 2^11 differ by at least 2^-22, so their keys
-    // differ by at least 1 (the numerator diff * 2^23 < 2^50 is exact in a double and
-    // the correctly rounded quotient is monotone).  Packing the lag below the key
-    // turns both selections into one 64-bit min / max.
-    unsigned long long kmin = ~0ULL, kmax = 0ULL;
-    for (int li = tid; li < nlag; li += THREADS) {
+    __syncwarp();
+    // ---- best / worst lag ----------------------------------------------------
+    unsigned bd = 0, wd = 0;
+    int bp = 0, wp = 0;
+    for (int li = lane; li < nlag; li += 32) {
       const int p = 4 * g0 + li;
       if (p >= lo && p <= hi) {
-        const double q = (double)((unsigned long long)acc[li] << 23) / (double)p;
-        const unsigned long long key = (unsigned long long)q;
-        const unsigned long long lo_key = (key << 11) | (unsigned)p;
-        const unsigned long long hi_key = (key << 11) | (unsigned)(2047 - p);
-        kmin = lo_key < kmin ? lo_key : kmin;
-        kmax = hi_key > kmax ? hi_key : kmax;
+        const unsigned d = acc[li];
+        if (bp == 0) {
+          bd = wd = d;
+          bp = wp = p;
+        } else {
+          // p is larger than the lags this lane already holds: strict comparisons
+          if ((unsigned long long)d * (unsigned)bp < (unsigned long long)bd * (unsigned)p) { bd = d; bp = p; }
+          if ((unsigned long long)d * (unsigned)wp > (unsigned long long)wd * (unsigned)p) { wd = d; wp = p; }
+        }
       }
     }
-#pragma unroll
-    for (int m = 16; m > 0; m >>= 1) {
-      const unsigned long long a = __shfl_xor_sync(0xffffffffu, kmin, m);
-      const unsigned long long b = __shfl_xor_sync(0xffffffffu, kmax, m);
-      kmin = a < kmin ? a : kmin;
-      kmax = b > kmax ? b : kmax;
-    }
-    if (NW > 1) {
-      if ((tid & 31) == 0) {
-        red[tid >> 5] = kmin;
-        red[NW + (tid >> 5)] = kmax;
-      }
-      __syncthreads();
-      kmin = red[0];
-      kmax = red[NW];
-#pragma unroll
-      for (int w = 1; w < NW; w++) {
-        kmin = red[w] < kmin ? red[w] : kmin;
-        kmax = red[NW + w] > kmax ? red[NW + w] : kmax;
-      }
-    }
-    const int best = (int)(kmin & 2047);
-    int worst = 2047 - (int)(kmax & 2047);
-    const unsigned best_diff = acc[best - 4 * g0];
-    unsigned worst_diff = acc[worst - 4 * g0];
-    __syncthreads();  // acc[] and red[] may be rewritten by the next search
+    unsigned best_diff, worst_diff;
+    int best, worst;
+    pick<true>(bd, bp, &best_diff, &best);
+    pick<false>(wd, wp, &worst_diff, &worst);
+    __syncwarp();  // acc[] is rewritten by the next search
     // the C scan starts from (maxDiff = 0, worstPeriod = 255) and only replaces
     // it with a strictly larger ratio
     if (worst_diff == 0u) worst = 255;
@@ -285,7 +302,7 @@ struct Sonic {
       stages = skip != 1 ? 2 : 1;
     }
     for (int stage = 0; stage < stages; stage++) {
-      period = search(arr, aoff, lo, hi, stage == 0 && stages == 2 ? map_coarse : map_fine, &minDiff, &maxDiff);
+      period = search(arr, aoff, lo, hi, stage == 0 && stages == 2, &minDiff, &maxDiff);
       if (stage == 0 && stages == 2) {
         // refine around the coarse estimate at the full rate (mono window)
         period *= skip;
@@ -372,24 +389,42 @@ struct Sonic {
   }
 };
 
-static __host__ __device__ inline int k4_acc_entries(const Geometry& g) {
+__host__ __device__ inline int k4_acc_entries(const Geometry& g) {
   int coarse = g.max_period / g.skip - g.min_period / g.skip + 1;
   int fine = g.skip != 1 ? 8 * g.skip + 1 : 0;
   int n = (coarse > fine ? coarse : fine) + 8;
   return (n + 3) & ~3;
 }
 
+// coarse work items: groups q = lo/4 .. hi/4, blocks 0 .. q (the last one masked)
+__host__ __device__ inline int k4_coarse_items(const Geometry& g) {
+  const int lo = g.min_period / g.skip, hi = g.max_period / g.skip;
+  int n = 0;
+  for (int q = lo >> 2; q <= (hi >> 2); q++) n += q + 1;
+  return n;
+}
+
+__host__ __device__ inline size_t k4_warp_smem(const Geometry& g, int buf_frames) {
+  size_t b = (size_t)(buf_frames + kPad) * sizeof(int);
+  b += (size_t)((g.max_required / g.skip + kPad + 3) & ~3) * sizeof(int);
+  b += (size_t)k4_acc_entries(g) * sizeof(unsigned);
+  b += (size_t)((k4_coarse_items(g) + 7) & ~7) * sizeof(unsigned short);
+  if (g.channels > 1) b += (size_t)buf_frames * g.channels * sizeof(short);
+  return (b + 15) & ~(size_t)15;
+}
+
 }  // namespace
 
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS) k4_sonic(K4Params p) {
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k4_sonic(K4Params p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int s = blockIdx.x;
+  const int warp = threadIdx.x >> 5;
+  const int s = blockIdx.x * WARPS + warp;
   if (s >= p.n_streams) return;
   const Geometry& g = p.g;
 
-  Sonic<THREADS> k;
-  k.tid = threadIdx.x;
+  Sonic k;
+  k.lane = threadIdx.x & 31;
   k.C = g.channels;
   k.S = g.step;
   k.minP = g.min_period;
@@ -398,26 +433,39 @@ __global__ void __launch_bounds__(THREADS) k4_sonic(K4Params p) {
   k.skip = g.skip;
   k.cap = p.out_capacity;
   k.bufN = p.buf_frames;
-  // carve-up (every piece a multiple of 16 bytes)
-  k.w32 = reinterpret_cast<int*>(smem_raw);
-  k.ds32 = k.w32 + k.bufN + 8;
-  k.acc = reinterpret_cast<unsigned*>(k.ds32 + ((k.maxReq / k.skip + 8 + 3) & ~3));
-  k.red = reinterpret_cast<unsigned long long*>(k.acc + k4_acc_entries(g));
-  k.buf = reinterpret_cast<short*>(k.red + 2 * Sonic<THREADS>::NW);
+  // carve-up of this warp's slice (every piece a multiple of 16 bytes)
+  unsigned char* base = smem_raw + (size_t)warp * k4_warp_smem(g, p.buf_frames);
+  k.w32 = reinterpret_cast<int*>(base);
+  k.ds32 = k.w32 + k.bufN + kPad;
+  k.acc = reinterpret_cast<unsigned*>(k.ds32 + ((k.maxReq / k.skip + kPad + 3) & ~3));
+  k.items = reinterpret_cast<unsigned short*>(k.acc + k4_acc_entries(g));
+  k.n_items = k4_coarse_items(g);
+  k.buf = reinterpret_cast<short*>(k.items + ((k.n_items + 7) & ~7));
   k.bufStart = 0;
   k.bufLen = 0;
+  k.dec_magic = (unsigned)((0x100000000ULL + (unsigned)(k.C * k.skip) - 1) / (unsigned)(k.C * k.skip));
   {
-    // lag groups per search stage (lags rounded out to multiples of four)
-    const bool two_stage = k.skip != 1;
+    // coarse item list and fine-pass lane mapping (lags rounded out to fours)
     const int c_lo = k.minP / k.skip, c_hi = k.maxP / k.skip;
-    const int full_groups = (c_hi >> 2) - (c_lo >> 2) + 1;
-    k.map_coarse.init(full_groups, threadIdx.x);
-    k.map_fine.init(two_stage ? 2 * k.skip + 2 : full_groups, threadIdx.x);
+    if (k.lane == 0) {
+      int w = 0;
+      for (int q = c_lo >> 2; q <= (c_hi >> 2); q++) {
+        for (int j = 0; j <= q; j++) k.items[w++] = (unsigned short)(((q - (c_lo >> 2)) << 8) | j);
+      }
+    }
+    const int fine_groups = k.skip != 1 ? 2 * k.skip + 2 : (c_hi >> 2) - (c_lo >> 2) + 1;
+    k.fG = 32 / fine_groups;
+    if (k.fG < 1) k.fG = 1;
+    k.fPerRound = 32 / k.fG;
+    k.fGi0 = k.lane / k.fG;
+    k.fg = k.lane - k.fGi0 * k.fG;
+    if (k.lane >= k.fPerRound * k.fG) k.fGi0 = 1 << 30;  // idle lane
   }
-  for (int i = threadIdx.x; i < 8; i += THREADS) {  // the over-read pads
+  for (int i = k.lane; i < kPad; i += 32) {  // the over-read pads
     k.w32[k.bufN + i] = 0;
     k.ds32[k.maxReq / k.skip + i] = 0;
   }
+  __syncwarp();
 
   const long long t_old = p.st.total[s];
   const long long t_new = p.flush ? t_old : t_old + (p.counts ? p.counts[s] : p.frames);
@@ -466,7 +514,9 @@ __global__ void __launch_bounds__(THREADS) k4_sonic(K4Params p) {
     if (ev_end < ev) ev_end = ev;
   }
   const long long n_events = (ev_end - ev) + (p.flush ? 1 : 0);
+  const bool per_frame_speed = nonlinear && !p.flush;
   long long expected = 0;
+  float speed_batch = 0.0f;  // 32 speeds at a time, one per lane
   for (long long i = 0; i < n_events; i++, ev++) {
     const bool final_flush = p.flush && i == n_events - 1;
     if (final_flush) {
@@ -477,7 +527,14 @@ __global__ void __launch_bounds__(THREADS) k4_sonic(K4Params p) {
       k.bufLen = 0;  // the window may hold real samples past the padding point
       k.fed += 2 * k.maxReq;
     } else if (nonlinear) {
-      if (!p.flush) speed = sp[ev - rA];
+      if (per_frame_speed) {
+        const int j = (int)(ev - rA);
+        if ((j & 31) == 0) {
+          const long long idx = (long long)j + k.lane;
+          speed_batch = idx < ev_end - rA ? sp[idx] : 0.0f;
+        }
+        speed = __shfl_sync(kFull, speed_batch, j & 31);
+      }
       k.fed = (ev + 1) * k.S;
     } else {
       k.fed = t_new;
@@ -495,7 +552,7 @@ __global__ void __launch_bounds__(THREADS) k4_sonic(K4Params p) {
     }
   }
 
-  if (threadIdx.x == 0) {
+  if (k.lane == 0) {
     p.st.sonic_head[s] = k.head;
     p.st.sonic_fed[s] = k.fed;
     p.st.out_total[s] = k.outTotal;
@@ -508,46 +565,35 @@ __global__ void __launch_bounds__(THREADS) k4_sonic(K4Params p) {
   }
 }
 
-static int k4_buf_frames(const Geometry& g) {
-  // window: several search spans, multiple of 64 frames
-  int n = 8 * g.max_required;
-  if (n < 4096) n = 4096;
+static int k4_buf_frames(const Geometry& g, int n_streams) {
+  // window: several search spans; smaller when many streams share an SM
+  int n = (n_streams >= 148 * 12 ? 4 : 8) * g.max_required;
+  const int floor_n = n_streams >= 148 * 12 ? 2048 : 4096;
+  if (n < floor_n) n = floor_n;
   if (const char* e = getenv("SPEEDY_K4_BUF")) n = atoi(e) > 2 * g.max_required ? atoi(e) : n;
   return (n + 63) & ~63;
 }
 
-static size_t k4_smem(const Geometry& g, int buf_frames, int nw) {
-  size_t b = (size_t)(buf_frames + 8) * sizeof(int);
-  b += (size_t)((g.max_required / g.skip + 8 + 3) & ~3) * sizeof(int);
-  b += (size_t)k4_acc_entries(g) * sizeof(unsigned);
-  b += (size_t)2 * nw * sizeof(unsigned long long);
-  if (g.channels > 1) b += (size_t)buf_frames * g.channels * sizeof(short);
-  return (b + 15) & ~(size_t)15;
-}
-
-template <int THREADS>
+template <int WARPS>
 static cudaError_t launch_k4_t(K4Params& p, cudaStream_t stream) {
-  const size_t smem = k4_smem(p.g, p.buf_frames, THREADS / 32);
+  const size_t smem = (size_t)WARPS * k4_warp_smem(p.g, p.buf_frames);
   static size_t attr = 0;
   if (smem > attr) {
-    cudaError_t e = cudaFuncSetAttribute(k4_sonic<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k4_sonic<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     attr = smem;
   }
-  k4_sonic<THREADS><<<p.n_streams, THREADS, smem, stream>>>(p);
+  const int blocks = (p.n_streams + WARPS - 1) / WARPS;
+  k4_sonic<WARPS><<<blocks, WARPS * 32, smem, stream>>>(p);
   count_launch();
   return cudaGetLastError();
 }
 
 cudaError_t launch_k4(const K4Params& p0, cudaStream_t stream) {
   K4Params p = p0;
-  p.buf_frames = k4_buf_frames(p.g);
-  int t = p.threads_per_stream;
-  if (t == 0) t = p.n_streams >= 148 * 16 ? 32 : 64;
-  if (t <= 32) return launch_k4_t<32>(p, stream);
-  if (t <= 64) return launch_k4_t<64>(p, stream);
-  return launch_k4_t<128>(p, stream);
+  p.buf_frames = k4_buf_frames(p.g, p.n_streams);
+  // one warp per stream; CTAs of one warp keep the grid fine-grained
+  return launch_k4_t<1>(p, stream);
 }
 
 }  // namespace speedy

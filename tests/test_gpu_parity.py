@@ -79,12 +79,11 @@ def test_features_tension_speed_tapestry(golden_inputs, match_matlab):
     assert rel_to_scale(taps["speed"][0], o["speed"]) < REL
 
 
-@pytest.mark.parametrize("tps", [32, 64, 128])
-@pytest.mark.parametrize("speed,feedback", [(3.0, 0.1), (2.0, 0.1), (1.5, 0.0), (3.5, 0.0)])
-def test_resynthesis_bit_exact_given_oracle_speeds(golden_inputs, speed, feedback, tps):
+@pytest.mark.parametrize("speed,feedback", [(3.0, 0.1), (2.0, 0.1), (1.5, 0.0), (3.5, 0.0), (1.05, 0.1), (6.0, 0.3)])
+def test_resynthesis_bit_exact_given_oracle_speeds(golden_inputs, speed, feedback):
     pcm, rate = golden_inputs["tapestry16k"]
     o = oracle_run(pcm, rate, speed, feedback=feedback)
-    outs, _, status = gpu_process(pcm[None], rate, speed, feedback=feedback, override=o["speed"][None], tps=tps)
+    outs, _, status = gpu_process(pcm[None], rate, speed, feedback=feedback, override=o["speed"][None])
     assert status[0] & ~sb.STATUS_FLUSHED == 0
     assert outs[0].shape == o["out"].shape, (outs[0].shape, o["out"].shape)
     assert np.array_equal(outs[0], o["out"])
@@ -206,3 +205,135 @@ def test_against_compiled_reference_fixtures(golden_inputs, golden_outputs):
         outs2, _, _ = gpu_process(pcm[None], r, float(speed), feedback=float(feedback), match_matlab=bool(kiss),
                                   override=case["speed"][None], taps=0)
         assert np.array_equal(outs2[0], case["out"]), name
+
+
+def test_drop_in_sonic_api(golden_inputs):
+    """The Sonic/Speedy C API (sonic2.h:54-125) through the drop-in: write in
+    1000-frame pieces as speedy_wave does (speedy_wave.cc:199-220), callbacks in
+    the reference's order, flush, drain."""
+    import ctypes as C
+    pcm, rate = golden_inputs["tapestry16k"]
+    L = sb.lib()
+    rec = {"tension": [], "speed": [], "features": [], "spec": [], "spec_t": [], "tension_t": [], "order": []}
+
+    @sb.tensionFunction
+    def on_t(stream, time, v):
+        rec["tension"].append(v); rec["tension_t"].append(time); rec["order"].append("t")
+
+    @sb.speedFunction
+    def on_s(stream, time, v):
+        rec["speed"].append(v); rec["order"].append("s")
+
+    @sb.featuresFunction
+    def on_f(stream, time, f):
+        rec["features"].append([f[i] for i in range(15)]); rec["order"].append("f")
+
+    @sb.spectrogramFunction
+    def on_g(stream, time, g):
+        rec["spec"].append(np.ctypeslib.as_array(g, shape=(480,)).copy()); rec["spec_t"].append(time)
+        rec["order"].append("g")
+
+    h = L.sonicCreateStream(rate, 1)
+    assert h
+    assert L.getSonicBufferSize(h) == 0 and L.sonicSpectrogramSize(h) == 480
+    L.sonicSetSpeed(h, 3.5)
+    L.sonicEnableNonlinearSpeedup(h, 1.0)
+    L.sonicSetDurationFeedbackStrength(h, 0.0)
+    L.sonicTensionCallback(h, on_t); L.sonicSpeedCallback(h, on_s)
+    L.sonicFeaturesCallback(h, on_f); L.sonicSpectrogramCallback(h, on_g)
+    out, buf = [], np.zeros(1000, np.int16)
+    x = np.ascontiguousarray(pcm[:, 0])
+    for t in range(0, len(x), 1000):
+        piece = np.ascontiguousarray(x[t:t + 1000])
+        assert L.sonicWriteShortToStream(h, piece.ctypes.data, len(piece)) == 1
+        n = L.sonicReadShortFromStream(h, buf.ctypes.data, 1000)
+        out.append(buf[:n].copy())
+    assert L.getSonicBufferSize(h) == 160
+    assert L.sonicFlushStream(h) == 1
+    while True:
+        n = L.sonicReadShortFromStream(h, buf.ctypes.data, 1000)
+        if n == 0:
+            break
+        out.append(buf[:n].copy())
+    assert L.sonicIntGetNumChannels(h) == 1
+    L.sonicDestroyStream(h)
+    out = np.concatenate(out)
+
+    o = oracle_run(pcm, rate, 3.5, feedback=0.0)   # the shipped library: Future = 12
+    assert len(rec["tension"]) == len(o["tension"]) and len(rec["spec"]) == o["spectrogram"].shape[0]
+    assert rec["spec_t"][:3] == [1, 2, 3] and rec["tension_t"][:3] == [0, 1, 2]
+    assert rel_to_scale(np.array(rec["tension"], np.float32), o["tension"]) < REL
+    assert rel_to_scale(np.array(rec["features"], np.float32)[:, 8], o["features"][:, 8]) < REL
+    peak = np.maximum(o["spectrogram"].max(axis=1, keepdims=True), 1e-12)
+    assert (np.abs(np.array(rec["spec"]) - o["spectrogram"]) / peak).max() < REL
+    # per frame: spectrogram, then (once ready) tension, features, speed
+    assert "".join(rec["order"]).replace("gtfs", "").strip("g") == ""
+    o2 = oracle_run(pcm, rate, 3.5, feedback=0.0, override=np.array(rec["speed"], np.float32))
+    assert np.array_equal(out, o2["out"][:, 0])
+
+
+def test_full_size_properties_config2_slice():
+    """BASELINE.json configs[1] geometry (16 kHz mono, 60 s, nonlinear 2.0x) at a size
+    the oracle cannot cover in seconds: size-independent properties plus an
+    oracle check on sampled streams."""
+    n, rate, secs = 256, 16000, 60
+    frames = rate * secs
+    d_in = torch.empty((n, frames, 1), dtype=torch.int16, device="cuda")
+    sb.synth_device(d_in, 0, n, rate, 1, frames)
+    cap = frames + 4096
+    b = sb.Batch(n, rate, 1, speed=2.0, nonlinear=1.0, feedback=0.1, max_write_frames=frames, out_capacity=cap,
+                 taps=sb.TAP_SPEED)
+    d_out = torch.zeros((n, cap, 1), dtype=torch.int16, device="cuda")
+    d_cnt = torch.zeros(n, dtype=torch.int32, device="cuda")
+    results = []
+    for _ in range(2):
+        b.reset()
+        b.write_device(d_in, frames, frames)
+        b.flush_device()
+        b.read_device(d_out, cap, d_cnt)
+        torch.cuda.synchronize()
+        results.append((d_out.cpu().numpy().copy(), d_cnt.cpu().numpy().copy()))
+    st = b.status()
+    speeds = b.taps()["speed"]
+    b.close()
+    out, cnt = results[0]
+    # idempotence: the same input twice gives the same bytes
+    assert np.array_equal(cnt, results[1][1]) and np.array_equal(out, results[1][0])
+    assert np.all(st == sb.STATUS_FLUSHED)
+    # Output length: classic Sonic does not track rapidly varying speeds exactly
+    # (the reference documents this, sonic_test.cc:1019-1039), so only loose bounds
+    # hold: never shorter than the requested per-frame speeds imply by more than a
+    # flush tail, and an overall ratio around the requested 2.0x.
+    for s in range(n):
+        expect = float(np.sum(160.0 / speeds[s].astype(np.float64)))
+        assert cnt[s] > 0.95 * expect - 2000 and cnt[s] < 1.35 * expect, (s, cnt[s], expect)
+    ratio = frames / cnt.astype(np.float64)
+    assert np.all(ratio > 1.4) and np.all(ratio < 2.2), (ratio.min(), ratio.max())
+    # nothing beyond the count is written, samples stay in range of the input peak
+    peak = int(d_in.abs().max().item())
+    assert int(np.abs(out).max()) <= peak
+    for s in (0, 17, n - 1):
+        assert not out[s, cnt[s]:].any()
+    # oracle on sampled streams, with the GPU's own speeds
+    host = d_in.cpu().numpy()
+    for s in (0, 101, n - 1):
+        o = oracle_run(host[s], rate, 2.0, override=speeds[s])
+        assert len(speeds[s]) == len(o["speed"])
+        assert np.array_equal(out[s, :cnt[s]], o["out"]), s
+
+
+def test_process_host_api_matches_device_path():
+    """speedyBatchProcess (host buffers, slab-pipelined) == write/flush/read."""
+    n, rate, frames = 80, 16000, 16000 * 5
+    pcm = ol.synth(300, n, rate, 1, frames)
+    cap = frames + 4096
+    b = sb.Batch(n, rate, 1, speed=2.5, nonlinear=1.0, feedback=0.1, max_write_frames=frames, out_capacity=cap)
+    out_a, cnt_a = b.process(pcm, cap)
+    b.reset()
+    b.write(pcm)
+    b.flush()
+    out_b, cnt_b = b.read(cap)
+    b.close()
+    assert np.array_equal(cnt_a, cnt_b)
+    for s in range(n):
+        assert np.array_equal(out_a[s, :cnt_a[s]], out_b[s, :cnt_b[s]]), s
