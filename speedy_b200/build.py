@@ -13,6 +13,8 @@ BUILD = os.path.join(HERE, "_build")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC,-O2,-Wall", "-I" + CSRC]
+if os.environ.get("SPEEDY_K4_TIMING"):
+    COMMON.append("-DK4_TIMING")  # developer build: per-phase cycle counters in k4_sonic
 
 # (source, extra flags).  The recurrence and Sonic kernels must round exactly as
 # the reference's C does, so they are built without FMA contraction.

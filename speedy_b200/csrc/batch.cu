@@ -104,6 +104,46 @@ __global__ void __launch_bounds__(256) read_copy_kernel(const int16_t* out, long
   }
 }
 
+// speedyBatchProcess: move what every stream produced since the last call,
+// out[s][done[s] .. upto[s]), straight into the caller's pinned host buffer (a
+// device-accessible pointer under unified addressing) with 16-byte stores where the
+// two sides are equally aligned; done[s] advances to upto[s].
+__global__ void __launch_bounds__(256) scatter_out_kernel(const int16_t* out, long long cap, int channels,
+                                                          const int* upto, const int* done, int16_t* dst,
+                                                          long long dst_stride, int n) {
+  // A small grid (the copy is PCIe-bound; it must not crowd the compute kernels out
+  // of the SMs): block b walks streams b, b + gridDim.x, ...
+  for (int s = blockIdx.x; s < n; s += gridDim.x) {
+    long long a = done[s], b = upto[s];
+    if (b > dst_stride) b = dst_stride;
+    const int16_t* src = out + ((size_t)s * cap + a) * channels;
+    int16_t* d = dst + ((size_t)s * dst_stride + a) * channels;
+    const long long total = (b - a) * channels;
+    if (total <= 0) continue;
+    const size_t ms = reinterpret_cast<size_t>(src) & 15, md = reinterpret_cast<size_t>(d) & 15;
+    if (ms == md) {
+      long long head = ms ? (long long)((16 - ms) >> 1) : 0;
+      if (head > total) head = total;
+      const long long nv = (total - head) / 8;
+      for (long long i = threadIdx.x; i < head; i += blockDim.x) d[i] = src[i];
+      const int4* sv = reinterpret_cast<const int4*>(src + head);
+      int4* dv = reinterpret_cast<int4*>(d + head);
+      for (long long i = threadIdx.x; i < nv; i += blockDim.x) dv[i] = sv[i];
+      for (long long i = head + nv * 8 + threadIdx.x; i < total; i += blockDim.x) d[i] = src[i];
+    } else {
+      for (long long i = threadIdx.x; i < total; i += blockDim.x) d[i] = src[i];
+    }
+  }
+}
+
+__global__ void scatter_advance_kernel(int n, const int* upto, int* done, long long dst_stride) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  long long b = upto[s];
+  if (b > dst_stride) b = dst_stride;
+  done[s] = (int)b;
+}
+
 __global__ void read_finish_kernel(int n, int* pending, int* status, int* counts, long long dst_stride) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n) return;
@@ -214,9 +254,13 @@ struct speedyBatchStruct {
   long long stage_frames;
   int32_t* d_counts_stage;
   int32_t* h_pinned_counts;
-  // child contexts used by speedyBatchProcess (slabs of streams, pipelined)
-  std::vector<speedyBatch> slabs;
-  long long slab_frames;
+  // speedyBatchProcess: double-buffered input chunks and the copy streams
+  int16_t* d_pipe[3];
+  long long pipe_chunk;
+  int pipe_ready;
+  cudaStream_t s_h2d, s_d2h;
+  int* d_snap[3];       // out_count snapshots per chunk
+  int* d_done;          // frames already delivered to the host
   // per-kernel timing (speedyBatchSetProfiling)
   int profiling;
   cudaEvent_t ev[6];
@@ -321,7 +365,8 @@ int speedyBatchNumStreams(speedyBatch b) { return b ? b->n : 0; }
 void speedyBatchDestroy(speedyBatch b) {
   if (!b) return;
   cudaSetDevice(b->cfg.device);
-  for (speedyBatch c : b->slabs) speedyBatchDestroy(c);
+  if (b->s_h2d) cudaStreamDestroy(b->s_h2d);
+  if (b->s_d2h) cudaStreamDestroy(b->s_d2h);
   for (void* p : b->allocs) cudaFree(p);
   if (b->h_pinned_counts) cudaFreeHost(b->h_pinned_counts);
   for (int i = 0; i < 6; i++) if (b->ev[i]) cudaEventDestroy(b->ev[i]);
@@ -354,7 +399,12 @@ speedyBatch speedyBatchCreate(const speedyBatchConfig* cfg) {
   b->d_counts_stage = nullptr;
   b->d_override = nullptr;
   b->override_stride = 0;
-  b->slab_frames = 0;
+  b->d_pipe[0] = b->d_pipe[1] = b->d_pipe[2] = nullptr;
+  b->pipe_chunk = 0;
+  b->pipe_ready = 0;
+  b->s_h2d = b->s_d2h = nullptr;
+  b->d_snap[0] = b->d_snap[1] = b->d_snap[2] = nullptr;
+  b->d_done = nullptr;
   b->profiling = 0;
   b->ev_recorded = 0;
   for (int i = 0; i < 6; i++) b->ev[i] = nullptr;
@@ -424,7 +474,7 @@ speedyBatch speedyBatchCreate(const speedyBatchConfig* cfg) {
   if (ok && (cfg->taps & SPEEDY_TAP_FEATURES)) ok = dev_alloc(b, &b->d_tap_features, tap_rows * kFeatureCount);
   if (ok && (cfg->taps & SPEEDY_TAP_TENSION)) ok = dev_alloc(b, &b->d_tap_tension, tap_rows);
   if (ok && (cfg->taps & SPEEDY_TAP_SPEED)) ok = dev_alloc(b, &b->d_tap_speed, tap_rows);
-  if (ok && cudaMallocHost((void**)&b->h_pinned_counts, sizeof(int32_t) * n) != cudaSuccess) {
+  if (ok && cudaMallocHost((void**)&b->h_pinned_counts, sizeof(int32_t) * 2 * n) != cudaSuccess) {
     ok = false;
     set_error("speedyBatchCreate: cudaMallocHost failed");
   }
@@ -759,10 +809,11 @@ int speedyBatchGetKernelTimes(speedyBatch b, float* ms5) {
   return 1;
 }
 
-// One-shot over host buffers.  The streams are cut into slabs, each a child
-// batch with its own CUDA stream, so that the host->device copy of slab i+1 and
-// the device->host copy of slab i-1 overlap the kernels of slab i (streams are
-// independent: no cross-slab dependency exists).
+// One-shot over host buffers, pipelined in TIME: the input is cut into chunks of a
+// few seconds; while chunk c is being processed (the ordinary streaming write, state
+// carried on the device, bit-identical to one big write) chunk c+1 is on its way in
+// and the output chunk c-1 produced is on its way out.  The host->device copies,
+// the kernels and the device->host copies run on three CUDA streams.
 int speedyBatchProcess(speedyBatch b, const int16_t* h_in, int64_t frames, int16_t* h_out,
                        int64_t out_stride_frames, int32_t* h_out_counts) {
   if (!b || !h_in || !h_out || frames < 1) return 0;
@@ -772,73 +823,165 @@ int speedyBatchProcess(speedyBatch b, const int16_t* h_in, int64_t frames, int16
   }
   CU_TRY(cudaSetDevice(b->cfg.device));
   const int n = b->n, C = b->g.channels;
-  int n_slabs = n >= 64 ? 8 : (n >= 8 ? 4 : 1);
-  if (const char* e = getenv("SPEEDY_B200_SLABS")) n_slabs = atoi(e) > 0 ? atoi(e) : n_slabs;
-  if (n_slabs > n) n_slabs = n;
-  const int per = (n + n_slabs - 1) / n_slabs;
-  if (b->slabs.empty() || b->slab_frames < frames || (int)b->slabs.size() != n_slabs) {
-    for (speedyBatch c : b->slabs) speedyBatchDestroy(c);
-    b->slabs.clear();
-    for (int i = 0; i < n_slabs; i++) {
-      speedyBatchConfig cfg = b->cfg;
-      cfg.num_streams = std::min(per, n - i * per);
-      cfg.max_write_frames = frames;
-      cfg.taps = 0;
-      speedyBatch c = speedyBatchCreate(&cfg);
-      if (!c) return 0;
-      b->slabs.push_back(c);
-      if (!ensure_stage(c, frames)) return 0;
+  long long chunk = (frames + 11) / 12;
+  if (const char* e = getenv("SPEEDY_B200_CHUNK_FRAMES")) chunk = atoll(e) > 0 ? atoll(e) : chunk;
+  if (chunk < 4 * b->g.rate / 10) chunk = 4 * b->g.rate / 10;  // at least 0.4 s of audio
+  chunk = (chunk + 7) & ~7LL;
+  if (chunk > frames) chunk = frames;
+  const int nchunks = (int)((frames + chunk - 1) / chunk);
+  if (!b->pipe_ready || b->pipe_chunk < chunk) {
+    for (int i = 0; i < 3; i++) {
+      if (!dev_alloc(b, &b->d_pipe[i], (size_t)n * chunk * C)) return 0;
     }
-    b->slab_frames = frames;
+    if (!b->pipe_ready) {
+      int prio_lo = 0, prio_hi = 0;
+      cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);  // the copy-out kernel yields to compute
+      CU_TRY(cudaStreamCreateWithFlags(&b->s_h2d, cudaStreamNonBlocking));
+      CU_TRY(cudaStreamCreateWithPriority(&b->s_d2h, cudaStreamNonBlocking, prio_lo));
+    }
+    b->pipe_chunk = chunk;
+    b->pipe_ready = 1;
   }
-  const size_t in_row = (size_t)frames * C * sizeof(int16_t);
-  std::vector<cudaEvent_t> done(n_slabs);
-  for (int i = 0; i < n_slabs; i++) {
-    speedyBatch c = b->slabs[i];
-    const int s0 = i * per;
-    cudaStream_t st = c->own_stream;
-    if (!reset_state(c, st)) return 0;
-    // per-stream parameters follow the parent's
-    CU_TRY(cudaMemcpyAsync(c->st.speed, b->st.speed + s0, sizeof(float) * c->n, cudaMemcpyDeviceToDevice, st));
-    CU_TRY(cudaMemcpyAsync(c->st.sonic_speed, b->st.speed + s0, sizeof(float) * c->n, cudaMemcpyDeviceToDevice, st));
-    CU_TRY(cudaMemcpyAsync(c->st.nonlinear, b->st.nonlinear + s0, sizeof(float) * c->n, cudaMemcpyDeviceToDevice, st));
-    CU_TRY(cudaMemcpyAsync(c->st.feedback, b->st.feedback + s0, sizeof(float) * c->n, cudaMemcpyDeviceToDevice, st));
-    CU_TRY(cudaMemcpy2DAsync(c->d_stage, in_row, h_in + (size_t)s0 * frames * C, in_row, in_row, c->n,
-                             cudaMemcpyHostToDevice, st));
-    if (!speedyBatchWriteDevice(c, c->d_stage, frames, frames, nullptr, st)) return 0;
-    if (!speedyBatchFlushDevice(c, st)) return 0;
-    CU_TRY(cudaMemcpyAsync(c->h_pinned_counts, c->st.out_count, sizeof(int32_t) * c->n, cudaMemcpyDeviceToHost, st));
-    CU_TRY(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
-    CU_TRY(cudaEventRecord(done[i], st));
+  cudaStream_t sc = b->own_stream;
+  if (!speedyBatchReset(b, sc)) return 0;
+  std::vector<cudaEvent_t> ev_in(nchunks), ev_done(nchunks), ev_out(nchunks);
+  const bool trace = getenv("SPEEDY_B200_TRACE") != nullptr;  // developer aid: per-chunk timeline
+  const unsigned ev_flags = trace ? cudaEventDefault : cudaEventDisableTiming;
+  cudaEvent_t ev_t0 = nullptr;
+  for (int c = 0; c < nchunks; c++) {
+    CU_TRY(cudaEventCreateWithFlags(&ev_in[c], ev_flags));
+    CU_TRY(cudaEventCreateWithFlags(&ev_done[c], ev_flags));
+    CU_TRY(cudaEventCreateWithFlags(&ev_out[c], ev_flags));
   }
+  if (trace) {
+    CU_TRY(cudaEventCreate(&ev_t0));
+    CU_TRY(cudaEventRecord(ev_t0, sc));
+    CU_TRY(cudaStreamWaitEvent(b->s_h2d, ev_t0, 0));
+  }
+  std::vector<long long> prev(n, 0);
   int ok = 1;
-  for (int i = 0; i < n_slabs; i++) {
-    speedyBatch c = b->slabs[i];
-    const int s0 = i * per;
-    cudaStream_t st = c->own_stream;
-    if (cudaEventSynchronize(done[i]) != cudaSuccess) ok = 0;
-    cudaEventDestroy(done[i]);
-    if (!ok) continue;
-    long long mx = 0;
-    for (int s = 0; s < c->n; s++) {
-      long long cnt = c->h_pinned_counts[s];
-      if (cnt > out_stride_frames) cnt = out_stride_frames;
-      if (h_out_counts) h_out_counts[s0 + s] = (int32_t)cnt;
-      if (cnt > mx) mx = cnt;
+  const size_t in_pitch = (size_t)frames * C * sizeof(int16_t);
+  const size_t out_dpitch = (size_t)out_stride_frames * C * sizeof(int16_t);
+  const size_t out_spitch = (size_t)b->out_capacity * C * sizeof(int16_t);
+  // Is the caller's output buffer pinned, i.e. addressable from the device?  Then
+  // each chunk's new output is stored straight into it by a kernel, ragged starts
+  // and all, with no host involvement; otherwise fall back to one rectangular
+  // device->host copy per chunk (which re-copies the spread between streams).
+  int16_t* h_out_dev = nullptr;
+  {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, h_out) == cudaSuccess && attr.type == cudaMemoryTypeHost &&
+        attr.devicePointer != nullptr && !getenv("SPEEDY_B200_NO_ZEROCOPY")) {
+      h_out_dev = static_cast<int16_t*>(attr.devicePointer);
     }
-    if (mx > 0) {
-      const size_t row = (size_t)mx * C * sizeof(int16_t);
-      if (cudaMemcpy2DAsync(h_out + (size_t)s0 * out_stride_frames * C, (size_t)out_stride_frames * C * sizeof(int16_t),
-                            c->d_out, (size_t)c->out_capacity * C * sizeof(int16_t), row, c->n,
-                            cudaMemcpyDeviceToHost, st) != cudaSuccess)
-        ok = 0;
-    }
-    read_finish_kernel<<<(c->n + 127) / 128, 128, 0, st>>>(c->n, c->st.out_count, c->st.status, c->d_counts_stage,
-                                                           out_stride_frames);
-    count_launch();
+    cudaGetLastError();  // a pageable pointer leaves a sticky-free error behind
   }
-  for (int i = 0; i < n_slabs; i++) {
-    if (cudaStreamSynchronize(b->slabs[i]->own_stream) != cudaSuccess) ok = 0;
+  if (h_out_dev && !b->d_done) {
+    for (int i = 0; i < 3; i++) {
+      if (!dev_alloc(b, &b->d_snap[i], n)) return 0;
+    }
+    if (!dev_alloc(b, &b->d_done, n)) return 0;
+  }
+  if (h_out_dev) CU_TRY(cudaMemsetAsync(b->d_done, 0, sizeof(int) * n, sc));
+  auto drain = [&](int c) -> int {
+    if (h_out_dev) {
+      // device-side scatter on the copy-out stream, ordered after chunk c's kernels
+      if (cudaStreamWaitEvent(b->s_d2h, ev_done[c], 0) != cudaSuccess) return 0;
+      const int blocks = n < 48 ? n : 48;
+      scatter_out_kernel<<<blocks, 256, 0, b->s_d2h>>>(b->d_out, b->out_capacity, C, b->d_snap[c % 3], b->d_done,
+                                                       h_out_dev, out_stride_frames, n);
+      scatter_advance_kernel<<<(n + 127) / 128, 128, 0, b->s_d2h>>>(n, b->d_snap[c % 3], b->d_done,
+                                                                    out_stride_frames);
+      count_launch();
+      count_launch();
+      return cudaGetLastError() == cudaSuccess;
+    }
+    if (cudaEventSynchronize(ev_done[c]) != cudaSuccess) return 0;
+    const int32_t* cnt = b->h_pinned_counts + (size_t)(c & 1) * n;
+    long long lo = 1LL << 60, hi = 0;
+    for (int s = 0; s < n; s++) {
+      long long now = cnt[s];
+      if (now > out_stride_frames) now = out_stride_frames;
+      if (prev[s] < lo) lo = prev[s];
+      if (now > hi) hi = now;
+      prev[s] = now;
+    }
+    if (hi > lo) {
+      if (cudaMemcpy2DAsync(h_out + lo * C, out_dpitch, b->d_out + lo * C, out_spitch,
+                            (size_t)(hi - lo) * C * sizeof(int16_t), n, cudaMemcpyDeviceToHost,
+                            b->s_d2h) != cudaSuccess)
+        return 0;
+    }
+    return 1;
+  };
+  // chunk c travels in staging buffer c % 3; its copy is enqueued two chunks ahead
+  // of its kernels so the host->device stream never runs dry
+  auto enqueue_h2d = [&](int c) -> int {
+    const long long f0 = (long long)c * chunk;
+    const long long fc = frames - f0 < chunk ? frames - f0 : chunk;
+    const size_t row = (size_t)fc * C * sizeof(int16_t);
+    if (c >= 3) CU_TRY(cudaStreamWaitEvent(b->s_h2d, ev_done[c - 3], 0));
+    CU_TRY(cudaMemcpy2DAsync(b->d_pipe[c % 3], (size_t)chunk * C * sizeof(int16_t), h_in + f0 * C, in_pitch, row, n,
+                             cudaMemcpyHostToDevice, b->s_h2d));
+    CU_TRY(cudaEventRecord(ev_in[c], b->s_h2d));
+    return 1;
+  };
+  for (int c = 0; c < 2 && c < nchunks && ok; c++) ok = enqueue_h2d(c);
+  for (int c = 0; c < nchunks && ok; c++) {
+    const long long f0 = (long long)c * chunk;
+    const long long fc = frames - f0 < chunk ? frames - f0 : chunk;
+    CU_TRY(cudaStreamWaitEvent(sc, ev_in[c], 0));
+    if (!speedyBatchWriteDevice(b, b->d_pipe[c % 3], chunk, fc, nullptr, sc)) ok = 0;
+    if (ok && c == nchunks - 1 && !speedyBatchFlushDevice(b, sc)) ok = 0;
+    if (h_out_dev) {
+      // the scatter of chunk c reads this snapshot while later chunks advance out_count;
+      // snapshot c % 3 is free again once the scatter of chunk c - 3 has run
+      if (c >= 3) CU_TRY(cudaStreamWaitEvent(sc, ev_out[c - 3], 0));
+      CU_TRY(cudaMemcpyAsync(b->d_snap[c % 3], b->st.out_count, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, sc));
+    }
+    if (!h_out_dev || c == nchunks - 1) {
+      CU_TRY(cudaMemcpyAsync(b->h_pinned_counts + (size_t)(c & 1) * n, b->st.out_count, sizeof(int32_t) * n,
+                             cudaMemcpyDeviceToHost, sc));
+    }
+    CU_TRY(cudaEventRecord(ev_done[c], sc));
+    if (ok && c + 2 < nchunks) ok = enqueue_h2d(c + 2);
+    if (h_out_dev) {
+      if (ok) ok = drain(c);
+      CU_TRY(cudaEventRecord(ev_out[c], b->s_d2h));
+    } else if (ok && c >= 1) {
+      ok = drain(c - 1);
+    }
+  }
+  if (ok && !h_out_dev) ok = drain(nchunks - 1);
+  if (ok && h_out_dev) {
+    if (cudaEventSynchronize(ev_done[nchunks - 1]) != cudaSuccess) ok = 0;
+    const int32_t* cnt = b->h_pinned_counts + (size_t)((nchunks - 1) & 1) * n;
+    for (int s = 0; s < n; s++) prev[s] = cnt[s] < out_stride_frames ? cnt[s] : out_stride_frames;
+  }
+  if (h_out_counts) {
+    for (int s = 0; s < n; s++) h_out_counts[s] = (int32_t)prev[s];
+  }
+  read_finish_kernel<<<(n + 127) / 128, 128, 0, sc>>>(n, b->st.out_count, b->st.status, b->d_counts_stage,
+                                                      out_stride_frames);
+  count_launch();
+  if (cudaStreamSynchronize(b->s_d2h) != cudaSuccess) ok = 0;
+  if (cudaStreamSynchronize(b->s_h2d) != cudaSuccess) ok = 0;
+  if (cudaStreamSynchronize(sc) != cudaSuccess) ok = 0;
+  if (trace) {
+    for (int c = 0; c < nchunks; c++) {
+      float a = 0, d = 0, o = 0;
+      cudaEventElapsedTime(&a, ev_t0, ev_in[c]);
+      cudaEventElapsedTime(&d, ev_t0, ev_done[c]);
+      if (h_out_dev) cudaEventElapsedTime(&o, ev_t0, ev_out[c]);
+      fprintf(stderr, "[speedyBatchProcess] chunk %2d: h2d done %7.2f ms, kernels done %7.2f ms, out done %7.2f ms\n", c,
+              a, d, o);
+    }
+    cudaEventDestroy(ev_t0);
+  }
+  for (int c = 0; c < nchunks; c++) {
+    cudaEventDestroy(ev_in[c]);
+    cudaEventDestroy(ev_done[c]);
+    cudaEventDestroy(ev_out[c]);
   }
   if (!ok) set_error(std::string("speedyBatchProcess: ") + cudaGetErrorString(cudaGetLastError()));
   return ok;

@@ -89,24 +89,33 @@ __device__ __forceinline__ void stage_mono(const Source& src, long long start, i
       const int nvec = (int)(c1 - c0);
       T* d = dst + (fv0 - start);
       short* r = raw16 ? raw16 + (fv0 - start) * C : nullptr;
-#pragma unroll 4
-      for (int v = tid; v < nvec; v += THREADS) {
-        const int4 q = vp[v];
-        const int w[4] = {q.x, q.y, q.z, q.w};
-        if (C == 1) {
+      for (int vb = tid; vb < nvec; vb += 4 * THREADS) {
+        int4 q4[4];
 #pragma unroll
-          for (int j = 0; j < 4; j++) {
-            d[v * 8 + 2 * j] = (T)(short)(w[j] & 0xffff);
-            d[v * 8 + 2 * j + 1] = (T)(short)(w[j] >> 16);
-          }
-        } else {
+        for (int u = 0; u < 4; u++) {  // four 16-byte loads in flight per thread
+          const int v = vb + u * THREADS;
+          q4[u] = v < nvec ? vp[v] : make_int4(0, 0, 0, 0);
+        }
 #pragma unroll
-          for (int j = 0; j < 4; j++) {
-            const int l = (short)(w[j] & 0xffff), h = (short)(w[j] >> 16);
-            d[v * 4 + j] = (T)((l + h) / 2);
-            if (r) {
-              r[(v * 4 + j) * 2] = (short)l;
-              r[(v * 4 + j) * 2 + 1] = (short)h;
+        for (int u = 0; u < 4; u++) {
+          const int v = vb + u * THREADS;
+          if (v >= nvec) continue;
+          const int w[4] = {q4[u].x, q4[u].y, q4[u].z, q4[u].w};
+          if (C == 1) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              d[v * 8 + 2 * j] = (T)(short)(w[j] & 0xffff);
+              d[v * 8 + 2 * j + 1] = (T)(short)(w[j] >> 16);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              const int l = (short)(w[j] & 0xffff), h = (short)(w[j] >> 16);
+              d[v * 4 + j] = (T)((l + h) / 2);
+              if (r) {
+                r[(v * 4 + j) * 2] = (short)l;
+                r[(v * 4 + j) * 2 + 1] = (short)h;
+              }
             }
           }
         }

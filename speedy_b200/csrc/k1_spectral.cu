@@ -131,24 +131,6 @@ __device__ __forceinline__ float inverse_norm(float energy) {
   return (float)(1.0 / (sqrt((double)energy) + (double)eps));
 }
 
-// speedy.c:705-719 in the log domain.  The reference sums, over the bins where both
-// spectra exceed max(cur)/100, |log((cur_i*inv_c + eps) / (last_i*inv_l + eps))|.
-// For those bins eps = 2.2e-16 is below half an ulp of the normalised value (which
-// is at least 0.01/sqrt(N/2)), so the term equals |log cur_i - log last_i +
-// (log inv_c - log inv_l)|; the logarithm of every magnitude is taken once, when
-// the magnitude is produced, instead of once per frame pair.
-//   lc/ll: log magnitudes of at_time a and a-1 (bin 0 unused); log_thr = log of
-//   max(cur)/100; dl = log inv_c - log inv_l.
-__device__ __forceinline__ float spectral_difference_log(const float* lc, const float* ll, int half,
-                                                         float log_thr, float dl, int lane) {
-  float acc = 0.0f;
-  for (int i = 1 + lane; i < half; i += 32) {
-    const float c = lc[i], l = ll[i];
-    if (c > log_thr && l > log_thr) acc += fabsf((c - l) + dl);
-  }
-  return warp_sum(acc);
-}
-
 // ---------------------------------------------------------------------------
 // 16 kHz fast path
 // ---------------------------------------------------------------------------
@@ -163,7 +145,7 @@ constexpr float kPreLo = (float)(0.97 - (double)0.97f);  // remainder of the dou
 
 struct WarpSmem480 {
   float2 z[2][240];      // per slot: windowed input (aliased), then transposes
-  float lmag[3][240];    // log |X| of the previous window, slot A, slot B
+  float lmag[3][240];    // log2 |X|^2 of the previous window, slot A, slot B
   short samp[kSampN + 8];
 };
 
@@ -301,8 +283,10 @@ __global__ void __launch_bounds__(WARPS * 32) k1_spectral_480(K1Params p) {
     }
     __syncwarp();
 
-    // ---- real-FFT split, magnitude, energy ---------------------------------
-    float e_slot[2], mx_slot[2];
+    // ---- real-FFT split, power, energy -------------------------------------
+    // The features need |X|^2 (energy) and log|X| (difference), never |X| itself:
+    // keep p = re^2 + im^2 and log2 p; the square root is taken only for the tap.
+    float e_slot[2], pmax_slot[2];
 #pragma unroll
     for (int slot = 0; slot < 2; slot++) {
       const int k = kk + slot;
@@ -313,42 +297,53 @@ __global__ void __launch_bounds__(WARPS * 32) k1_spectral_480(K1Params p) {
       float e = 0.0f, mx = 0.0f;
       for (int kb = lane; kb < H16; kb += 32) {
         float2 zk = Z[kb];
-        float2 zm = Z[(240 - kb) % 240];
+        float2 zm = Z[kb == 0 ? 0 : 240 - kb];
         float2 zc = make_float2(zm.x, -zm.y);
         float2 sum = cscale(cadd(zk, zc), 0.5f);
         float2 dif = cscale(csub(zk, zc), 0.5f);
         float2 wd = mul_mi(cmul(s_tw480[kb], dif));
         float re = sum.x + wd.x, im = sum.y + wd.y;
-        // speedy.c:434-436: sqrt(r*r + i*i), products and sum rounded to float
-        float m = __fsqrt_rn(__fadd_rn(__fmul_rn(re, re), __fmul_rn(im, im)));
-        lmag[kb] = logf(m);
+        // speedy.c:434-436 squares and sums in float; so does this
+        const float pw = __fadd_rn(__fmul_rn(re, re), __fmul_rn(im, im));
+        lmag[kb] = __log2f(pw);
         if (kb >= 1) {
-          e += m * m;
-          mx = fmaxf(mx, m);
+          e += pw;
+          mx = fmaxf(mx, pw);
         }
         if (tap) {
+          const float m = __fsqrt_rn(pw);
           tap[kb] = m;
           if (kb >= 1) tap[480 - kb] = m;
           if (kb == 0) tap[240] = fabsf(zk.x - zk.y);  // X[N/2] = Re(Z0) - Im(Z0)
         }
       }
       e_slot[slot] = warp_sum(e);
-      mx_slot[slot] = warp_max(mx);
+      pmax_slot[slot] = warp_max(mx);
     }
     __syncwarp();
 
     // ---- spectral difference against the previous window, outputs ---------
+    // speedy.c:705-719 in the log2 domain: with n_i = |X_i| / (sqrt(E) + eps),
+    //   log(n_c / n_l) = ln2 * (0.5 (lp_c - lp_l) + (linv_c - linv_l)),
+    //   lp = log2 |X|^2, linv = -log2(sqrt(E) + eps);
+    // |X_i| > max|X| / 100 (speedy.c:709, 714)  <=>  lp_i > log2(max p) - log2(1e4).
     float linv_slot[2];
 #pragma unroll
     for (int slot = 0; slot < 2; slot++) {
       const int k = kk + slot;
-      linv_slot[slot] = logf(inverse_norm(e_slot[slot]));
+      linv_slot[slot] = -__log2f(__fsqrt_rn(e_slot[slot]) + 2.2204e-16f);
       const float* lc = ws.lmag[slot == 0 ? ia : ib];
       const float* ll = ws.lmag[slot == 0 ? ip : ia];
       const float linv_last = slot == 0 ? linv_prev : linv_slot[0];
       if (k >= k0 && k < k1) {
-        const float log_thr = logf((float)((double)mx_slot[slot] / 100.0));  // speedy.c:709
-        float lsd = spectral_difference_log(lc, ll, H16, log_thr, linv_slot[slot] - linv_last, lane);
+        const float thr = __log2f(pmax_slot[slot]) - 13.287712379549449f;  // log2(1e4)
+        const float d2 = 2.0f * (linv_slot[slot] - linv_last);
+        float acc = 0.0f;
+        for (int i = 1 + lane; i < H16; i += 32) {
+          const float c = lc[i], l = ll[i];
+          if (c > thr && l > thr) acc += fabsf((c - l) + d2);
+        }
+        const float lsd = warp_sum(acc) * 0.34657359027997264f;  // ln2 / 2
         const int j = k - kA;
         if (lane == 0) p.feat[(size_t)s * p.feat_stride + j] = make_float2(e_slot[slot], lsd);
       }

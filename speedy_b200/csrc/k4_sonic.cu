@@ -34,7 +34,9 @@
 // at a multiple of four: for an aligned block of four samples a[blk..blk+3] the
 // operands of lags 4k..4k+3 are the seven values b[blk+4k .. blk+4k+6], i.e. two
 // more aligned LDS.128: 3 loads + 16 VABSDIFF per 16 differences.  The first and
-// last block of a lag group are the same code under a per-element mask.
+// last block of a lag group are the same code under a per-element mask.  A group's
+// blocks are spread over a few adjacent lanes, which keep their partial sums in
+// registers and combine them with shuffles; no shared-memory accumulators.
 #include <stdlib.h>
 
 #include "kernels.cuh"
@@ -43,7 +45,16 @@ namespace speedy {
 
 namespace {
 
-constexpr int kPad = 16;  // over-read slack behind the window and the decimated copy
+#ifdef K4_TIMING
+__device__ unsigned long long g_k4_cycles[16];
+#define T_BEGIN() const long long _t0 = clock64()
+#define T_END(slot) do { if (lane == 0 && timing) atomicAdd(&g_k4_cycles[slot], (unsigned long long)(clock64() - _t0)); } while (0)
+#else
+#define T_BEGIN() do {} while (0)
+#define T_END(slot) do {} while (0)
+#endif
+
+constexpr int kPad = 32;  // over-read slack behind the window and the decimated copy
 constexpr unsigned kFull = 0xffffffffu;
 
 struct Sonic {
@@ -54,9 +65,6 @@ struct Sonic {
   int* w32;                 // mono window, 32-bit [bufN + kPad]
   short* buf;               // interleaved raw window (C > 1 only) [bufN * C]
   int* ds32;                // decimated mono [maxReq / skip + kPad]
-  unsigned* acc;            // per-lag AMDF sums
-  unsigned short* items;    // coarse pass: work item -> (group << 8 | block)
-  int n_items;
   int bufN;
   // window state (warp-uniform)
   long long bufStart;
@@ -69,18 +77,23 @@ struct Sonic {
   int prevPeriod, prevMinDiff, remCopy, outCount, status;
   short* out;
   int lane;
-  // fine-pass lane mapping: G sub-lanes per lag group
+  // fine-pass lane mapping: fG sub-lanes per lag group
   int fG, fPerRound, fGi0, fg;
+  // coarse-pass lane mapping: group cGi (-1 = idle), sub-lane cSub of cG, largest cG
+  int cGi, cSub, cG, cMaxG;
   unsigned dec_magic;
+  bool timing;
 
   // Make [start, start + count) resident in the shared window (count <= bufN - 8).
   __device__ __forceinline__ void ensure(long long start, int count) {
     if (start >= bufStart && start + count <= bufStart + bufLen) return;
+    T_BEGIN();
     __syncwarp();  // every lane is done with the old window
     bufStart = start & ~7LL;  // keeps the 16-byte loads of the refill aligned
     bufLen = bufN;
     stage_mono<32, int>(src, bufStart, bufN, zero_from, w32, C > 1 ? buf : nullptr, lane);
     __syncwarp();
+    T_END(0);
   }
 
   __device__ __forceinline__ void advance_out(int n) {
@@ -100,6 +113,7 @@ struct Sonic {
     const long long base = (long long)(outCount + out_offset_frames) * C;
     const long long room = cap * C - base;
     short* o = out + base;
+    T_BEGIN();
     if (C == 1) {
       for (int i = lane; i < total; i += 32) {
         if (i < room) o[i] = (short)w32[o0 + i];
@@ -110,6 +124,20 @@ struct Sonic {
         if (i < room) o[i] = p[i];
       }
     }
+    T_END(7);
+  }
+
+  // Truncating num / n for |num| < 2^25, 0 < n < 2^11: the float quotient is within
+  // one of the true one, two fix-up steps make it exact.
+  static __device__ __forceinline__ int div_trunc(int num, int n, float rcp_n) {
+    const int an = abs(num);
+    int q = (int)((float)an * rcp_n);
+    int rem = an - q * n;
+    if (rem < 0) { q--; rem += n; }
+    if (rem < 0) { q--; rem += n; }
+    if (rem >= n) { q++; rem -= n; }
+    if (rem >= n) { q++; }
+    return num < 0 ? -q : q;
   }
 
   // out[t] = (down[t]*(n-t) + up[t]*t) / n per channel, C integer arithmetic.
@@ -120,9 +148,11 @@ struct Sonic {
     const long long base = (long long)(outCount + out_offset_frames) * C;
     const long long room = cap * C - base;
     short* o = out + base;
+    T_BEGIN();
+    const float rcp_n = __frcp_rn((float)(n > 0 ? n : 1));
     if (C == 1) {
       for (int t = lane; t < total; t += 32) {
-        int v = (w32[d0 + t] * (n - t) + w32[u0 + t] * t) / n;
+        int v = div_trunc(w32[d0 + t] * (n - t) + w32[u0 + t] * t, n, rcp_n);
         if (t < room) o[t] = (short)v;
       }
     } else {
@@ -130,96 +160,182 @@ struct Sonic {
       const short* up_ = buf + (size_t)u0 * C;
       for (int i = lane; i < total; i += 32) {
         int t = i / C;
-        int v = ((int)dp[i] * (n - t) + (int)up_[i] * t) / n;
+        int v = div_trunc((int)dp[i] * (n - t) + (int)up_[i] * t, n, rcp_n);
         if (i < room) o[i] = (short)v;
       }
     }
+    T_END(6);
   }
 
   // Upstream downSampleInput: sum `skip` frames x C channels, C integer division
   // (truncating).  |sum| < 2^21 and the divisor is small, so the quotient is exact
   // as (|sum| * ceil(2^32 / divisor)) >> 32.
   __device__ __forceinline__ void decimate(int off) {
+    T_BEGIN();
     const int count = maxReq / skip;
     const int per = C * skip;
-    for (int i = lane; i < count; i += 32) {
-      int v = 0;
-      if (C == 1) {
-        const int* q = w32 + off + i * skip;
-        for (int j = 0; j < skip; j++) v += q[j];
-      } else {
-        const short* q = buf + ((size_t)off + (size_t)i * skip) * C;
-        for (int j = 0; j < per; j++) v += q[j];
+    if (C == 1 && (skip == 2 || skip == 4 || skip == 8)) {
+      // conflict-free rows of 32 consecutive samples; the `skip`-sums are segmented
+      // sums over adjacent lanes, left in the first lane of every segment
+      const int rows = (count * skip + 31) >> 5;
+      for (int r0 = 0; r0 < rows; r0 += 4) {
+        int v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {  // four independent rows in flight
+          // (reads past the last frame land in the pad: those sums are not stored)
+          v[u] = r0 + u < rows ? w32[off + 32 * (r0 + u) + lane] : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          v[u] += __shfl_down_sync(kFull, v[u], 1);
+          if (skip >= 4) v[u] += __shfl_down_sync(kFull, v[u], 2);
+          if (skip >= 8) v[u] += __shfl_down_sync(kFull, v[u], 4);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int i = (32 * (r0 + u) + lane) >> (skip == 2 ? 1 : (skip == 4 ? 2 : 3));
+          const int qa = (int)__umulhi((unsigned)abs(v[u]), dec_magic);
+          if ((lane & (skip - 1)) == 0 && i < count) ds32[i] = v[u] < 0 ? -qa : qa;
+        }
       }
-      const int qa = (int)__umulhi((unsigned)abs(v), dec_magic);
-      ds32[i] = v < 0 ? -qa : qa;
+    } else {
+      for (int i = lane; i < count; i += 32) {
+        int v = 0;
+        if (C == 1) {
+          const int* q = w32 + off + i * skip;
+          int j = 0;
+          for (; j + 4 <= skip; j += 4) v += (q[j] + q[j + 1]) + (q[j + 2] + q[j + 3]);
+          for (; j < skip; j++) v += q[j];
+        } else {
+          const short* q = buf + ((size_t)off + (size_t)i * skip) * C;
+          int j = 0;
+          for (; j + 4 <= per; j += 4) v += (q[j] + q[j + 1]) + (q[j + 2] + q[j + 3]);
+          for (; j < per; j++) v += q[j];
+        }
+        const int qa = (int)__umulhi((unsigned)abs(v), dec_magic);
+        ds32[i] = v < 0 ? -qa : qa;
+      }
     }
     __syncwarp();
+    T_END(1);
   }
 
   // |a - b| sums of one aligned block of four samples for the four lags
-  // pg .. pg+3 (pg a multiple of four).  Sample x = blk + m contributes to lag
-  // pg + l iff off <= x < off + pg + l.
-  __device__ __forceinline__ void block_sads(const int* arr, int blk, int pg, int off, unsigned (&d)[4]) {
+  // pg .. pg+3 (pg a multiple of four), every sample valid for every lag.
+  __device__ __forceinline__ void block_full(const int* arr, int blk, int pg, unsigned (&d)[4]) {
     const int4 av = *reinterpret_cast<const int4*>(arr + blk);
     const int4 b0 = *reinterpret_cast<const int4*>(arr + blk + pg);
     const int4 b1 = *reinterpret_cast<const int4*>(arr + blk + pg + 4);
-    if (blk >= off && blk + 3 < off + pg) {
-      d[0] = __sad(av.x, b0.x, d[0]); d[0] = __sad(av.y, b0.y, d[0]);
-      d[0] = __sad(av.z, b0.z, d[0]); d[0] = __sad(av.w, b0.w, d[0]);
-      d[1] = __sad(av.x, b0.y, d[1]); d[1] = __sad(av.y, b0.z, d[1]);
-      d[1] = __sad(av.z, b0.w, d[1]); d[1] = __sad(av.w, b1.x, d[1]);
-      d[2] = __sad(av.x, b0.z, d[2]); d[2] = __sad(av.y, b0.w, d[2]);
-      d[2] = __sad(av.z, b1.x, d[2]); d[2] = __sad(av.w, b1.y, d[2]);
-      d[3] = __sad(av.x, b0.w, d[3]); d[3] = __sad(av.y, b1.x, d[3]);
-      d[3] = __sad(av.z, b1.y, d[3]); d[3] = __sad(av.w, b1.z, d[3]);
-    } else {
-      const int a[4] = {av.x, av.y, av.z, av.w};
-      const int b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-      const int first = off - blk;      // m >= first
-      const int last = off + pg - blk;  // m < last + l
+    d[0] = __sad(av.x, b0.x, d[0]); d[0] = __sad(av.y, b0.y, d[0]);
+    d[0] = __sad(av.z, b0.z, d[0]); d[0] = __sad(av.w, b0.w, d[0]);
+    d[1] = __sad(av.x, b0.y, d[1]); d[1] = __sad(av.y, b0.z, d[1]);
+    d[1] = __sad(av.z, b0.w, d[1]); d[1] = __sad(av.w, b1.x, d[1]);
+    d[2] = __sad(av.x, b0.z, d[2]); d[2] = __sad(av.y, b0.w, d[2]);
+    d[2] = __sad(av.z, b1.x, d[2]); d[2] = __sad(av.w, b1.y, d[2]);
+    d[3] = __sad(av.x, b0.w, d[3]); d[3] = __sad(av.y, b1.x, d[3]);
+    d[3] = __sad(av.z, b1.y, d[3]); d[3] = __sad(av.w, b1.z, d[3]);
+  }
+
+  // The same for a block at the edge of the range: sample x = blk + m contributes to
+  // lag pg + l iff off <= x < off + pg + l.
+  __device__ __forceinline__ void block_edge(const int* arr, int blk, int pg, int off, unsigned (&d)[4]) {
+    const int4 av = *reinterpret_cast<const int4*>(arr + blk);
+    const int4 b0 = *reinterpret_cast<const int4*>(arr + blk + pg);
+    const int4 b1 = *reinterpret_cast<const int4*>(arr + blk + pg + 4);
+    const int a[4] = {av.x, av.y, av.z, av.w};
+    const int b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    const int first = off - blk;      // m >= first
+    const int last = off + pg - blk;  // m < last + l
 #pragma unroll
-      for (int l = 0; l < 4; l++) {
+    for (int l = 0; l < 4; l++) {
 #pragma unroll
-        for (int m = 0; m < 4; m++) {
-          if (m >= first && m < last + l) d[l] = __sad(a[m], b[m + l], d[l]);
+      for (int m = 0; m < 4; m++) {
+        if (m >= first && m < last + l) d[l] = __sad(a[m], b[m + l], d[l]);
+      }
+    }
+  }
+
+  // Exact arg-min and arg-max of diff/period over the warp's candidates (one
+  // (diff, period) pair per lane for each, period 0 = none).  The C scan compares by
+  // cross-multiplication with strict inequalities, so ties go to the smaller lag.
+  // A float quotient picks the lanes within 2e-6 of the extremum (a superset of the
+  // true extremum: its relative error is below 4e-7); almost always that is one
+  // lane, otherwise the short list is resolved exactly.
+  __device__ __forceinline__ void pick2(unsigned bd, int bp, unsigned wd, int wp, unsigned* min_diff,
+                                        int* min_period, unsigned* max_diff, int* max_period) {
+    const float fb = bp ? __fdividef((float)bd, (float)bp) : 3.0e38f;
+    const float fw = wp ? __fdividef((float)wd, (float)wp) : 0.0f;
+    const float emin = __uint_as_float(__reduce_min_sync(kFull, __float_as_uint(fb)));
+    const float emax = __uint_as_float(__reduce_max_sync(kFull, __float_as_uint(fw)));
+    unsigned ballot_b = __ballot_sync(kFull, bp != 0 && fb <= emin * 1.000002f);
+    unsigned ballot_w = __ballot_sync(kFull, wp != 0 && fw >= emax * 0.999998f);
+    int sb = __ffs(ballot_b) - 1, sw = __ffs(ballot_w) - 1;
+    unsigned rbd = __shfl_sync(kFull, bd, sb);
+    int rbp = __shfl_sync(kFull, bp, sb);
+    unsigned rwd = __shfl_sync(kFull, wd, sw);
+    int rwp = __shfl_sync(kFull, wp, sw);
+    ballot_b &= ballot_b - 1;
+    ballot_w &= ballot_w - 1;
+    while (ballot_b) {  // rare: several candidates within rounding of each other
+      sb = __ffs(ballot_b) - 1;
+      ballot_b &= ballot_b - 1;
+      const unsigned cd = __shfl_sync(kFull, bd, sb);
+      const int cp = __shfl_sync(kFull, bp, sb);
+      const unsigned long long l = (unsigned long long)cd * (unsigned)rbp;
+      const unsigned long long r = (unsigned long long)rbd * (unsigned)cp;
+      if (l < r || (l == r && cp < rbp)) { rbd = cd; rbp = cp; }
+    }
+    while (ballot_w) {
+      sw = __ffs(ballot_w) - 1;
+      ballot_w &= ballot_w - 1;
+      const unsigned cd = __shfl_sync(kFull, wd, sw);
+      const int cp = __shfl_sync(kFull, wp, sw);
+      const unsigned long long l = (unsigned long long)cd * (unsigned)rwp;
+      const unsigned long long r = (unsigned long long)rwd * (unsigned)cp;
+      if (l > r || (l == r && cp < rwp)) { rwd = cd; rwp = cp; }
+    }
+    *min_diff = rbd; *min_period = rbp; *max_diff = rwd; *max_period = rwp;
+  }
+
+  // floor(a / b) for a < 2^27, 0 < b < 2^11 (quotient < 2^16): float estimate + fix-up.
+  static __device__ __forceinline__ int udiv_small(unsigned a, int b) {
+    int q = (int)((float)a * __frcp_rn((float)b));
+    int rem = (int)a - q * b;
+    if (rem < 0) { q--; rem += b; }
+    if (rem < 0) { q--; rem += b; }
+    if (rem >= b) { q++; rem -= b; }
+    if (rem >= b) { q++; }
+    return q;
+  }
+
+  // Fold the four lag sums a lane holds (lags pg .. pg+3) into its running best /
+  // worst candidates; lags ascend, so strict comparisons reproduce the C scan.
+  __device__ __forceinline__ void fold(const unsigned (&d)[4], int pg, int lo, int hi, unsigned& bd, int& bp,
+                                       unsigned& wd, int& wp) {
+#pragma unroll
+    for (int l = 0; l < 4; l++) {
+      const int p = pg + l;
+      if (p >= lo && p <= hi) {
+        if (bp == 0) {
+          bd = wd = d[l];
+          bp = wp = p;
+        } else {
+          if ((unsigned long long)d[l] * (unsigned)bp < (unsigned long long)bd * (unsigned)p) { bd = d[l]; bp = p; }
+          if ((unsigned long long)d[l] * (unsigned)wp > (unsigned long long)wd * (unsigned)p) { wd = d[l]; wp = p; }
         }
       }
     }
   }
 
-  // Exact arg-min / arg-max of diff/period over the warp's candidates (one per
-  // lane, period 0 = none).  The C scan compares by cross-multiplication with
-  // strict inequalities, so ties go to the smaller lag.  A float quotient picks
-  // the lanes within 2e-6 of the extremum (a superset of the true extremum, its
-  // relative error is below 4e-7); almost always that is one lane, otherwise the
-  // short list is resolved exactly.
-  template <bool kMin>
-  __device__ __forceinline__ void pick(unsigned diff, int period, unsigned* out_diff, int* out_period) {
-    const float f = period ? __fdividef((float)diff, (float)period) : (kMin ? 3.0e38f : 0.0f);
-    const unsigned key = __float_as_uint(f);
-    const float ext = __uint_as_float(kMin ? __reduce_min_sync(kFull, key) : __reduce_max_sync(kFull, key));
-    const bool near = period != 0 && (kMin ? f <= ext * 1.000002f : f >= ext * 0.999998f);
-    unsigned ballot = __ballot_sync(kFull, near);
-    int src_lane = __ffs(ballot) - 1;
-    unsigned bd = __shfl_sync(kFull, diff, src_lane);
-    int bp = __shfl_sync(kFull, period, src_lane);
-    ballot &= ballot - 1;
-    while (ballot) {  // rare: several candidates within rounding of each other
-      src_lane = __ffs(ballot) - 1;
-      ballot &= ballot - 1;
-      const unsigned cd = __shfl_sync(kFull, diff, src_lane);
-      const int cp = __shfl_sync(kFull, period, src_lane);
-      const unsigned long long l = (unsigned long long)cd * (unsigned)bp;
-      const unsigned long long r = (unsigned long long)bd * (unsigned)cp;
-      const bool better = kMin ? (l < r || (l == r && cp < bp)) : (l > r || (l == r && cp < bp));
-      if (better) {
-        bd = cd;
-        bp = cp;
+  // Sum the partial lag sums of the `G` adjacent lanes of a group into its first lane.
+  __device__ __forceinline__ void combine(unsigned (&d)[4], int sub, int G, int maxG) {
+    for (int delta = 1; delta < maxG; delta <<= 1) {
+#pragma unroll
+      for (int l = 0; l < 4; l++) {
+        const unsigned t = __shfl_down_sync(kFull, d[l], delta);
+        if (sub + delta < G) d[l] += t;
       }
     }
-    *out_diff = bd;
-    *out_period = bp;
   }
 
   // AMDF over lags lo..hi on a[i] = arr[off + i].  Returns the best lag; *minDiff /
@@ -228,62 +344,76 @@ struct Sonic {
                                         int* maxDiff) {
     const int g0 = lo >> 2;  // first lag group (lags 4*g0 .. 4*g0+3)
     const int ngroups = (hi >> 2) - g0 + 1;
-    const int nlag = ngroups * 4;
-    for (int li = lane; li < nlag; li += 32) acc[li] = 0;
-    __syncwarp();
-    if (coarse) {
-      // off == 0 and the lag range is fixed: a precomputed flat list of blocks
-      for (int w = lane; w < n_items; w += 32) {
-        const int it = items[w];
-        const int gi = it >> 8, j = it & 255;
-        unsigned d[4] = {0u, 0u, 0u, 0u};
-        block_sads(arr, 4 * j, 4 * (g0 + gi), 0, d);
-        atomicAdd(&acc[4 * gi + 0], d[0]);
-        atomicAdd(&acc[4 * gi + 1], d[1]);
-        atomicAdd(&acc[4 * gi + 2], d[2]);
-        atomicAdd(&acc[4 * gi + 3], d[3]);
-      }
-    } else {
-      const int B0 = off & ~3;
-      for (int gi = fGi0; gi < ngroups; gi += fPerRound) {
-        const int pg = 4 * (g0 + gi);
-        const int nblk = ((((off + pg + 2) & ~3) + 4) - B0) >> 2;
-        unsigned d[4] = {0u, 0u, 0u, 0u};
-        for (int j = fg; j < nblk; j += fG) block_sads(arr, B0 + 4 * j, pg, off, d);
-        atomicAdd(&acc[4 * gi + 0], d[0]);
-        atomicAdd(&acc[4 * gi + 1], d[1]);
-        atomicAdd(&acc[4 * gi + 2], d[2]);
-        atomicAdd(&acc[4 * gi + 3], d[3]);
-      }
-    }
-    __syncwarp();
-    // ---- best / worst lag ----------------------------------------------------
+    T_BEGIN();
     unsigned bd = 0, wd = 0;
     int bp = 0, wp = 0;
-    for (int li = lane; li < nlag; li += 32) {
-      const int p = 4 * g0 + li;
-      if (p >= lo && p <= hi) {
-        const unsigned d = acc[li];
-        if (bp == 0) {
-          bd = wd = d;
-          bp = wp = p;
-        } else {
-          // p is larger than the lags this lane already holds: strict comparisons
-          if ((unsigned long long)d * (unsigned)bp < (unsigned long long)bd * (unsigned)p) { bd = d; bp = p; }
-          if ((unsigned long long)d * (unsigned)wp > (unsigned long long)wd * (unsigned)p) { wd = d; wp = p; }
+    if (coarse) {
+      // off == 0 and the lag range is fixed: a static lane assignment with more
+      // lanes for the longer lags; group q has q fully valid blocks (j < q) and one
+      // partially valid block (j == q: sample m counts for lag 4q + l while m < l)
+      unsigned d[4] = {0u, 0u, 0u, 0u}, e[4] = {0u, 0u, 0u, 0u};
+      const int q = g0 + cGi;
+      const int pg = 4 * q;
+      if (cGi >= 0) {
+        int j = cSub;
+        for (; j + cG < q; j += 2 * cG) {
+          block_full(arr, 4 * j, pg, d);
+          block_full(arr, 4 * (j + cG), pg, e);
         }
+        if (j < q) block_full(arr, 4 * j, pg, d);
+        if (cSub == cG - 1) block_edge(arr, pg, pg, 0, e);
+#pragma unroll
+        for (int l = 0; l < 4; l++) d[l] += e[l];
+      }
+      combine(d, cSub, cG, cMaxG);
+      if (cGi >= 0 && cSub == 0) fold(d, pg, lo, hi, bd, bp, wd, wp);
+    } else {
+      // blocks of group gi: j = 0 .. nblk-1 at B0 + 4j; fully valid for jf0 <= j < jf1,
+      // the head block (j = 0 when off is unaligned) and one or two tail blocks are
+      // handled by the group's sub-lanes under a per-element mask
+      const int B0 = off & ~3;
+      const int jf0 = (off & 3) ? 1 : 0;
+      const int rounds = (ngroups + fPerRound - 1) / fPerRound;
+      for (int round = 0; round < rounds; round++) {
+        const int gi = fGi0 + round * fPerRound;
+        const bool live = gi < ngroups;  // also false for idle lanes
+        const int pg = 4 * (g0 + gi);
+        unsigned d[4] = {0u, 0u, 0u, 0u}, e[4] = {0u, 0u, 0u, 0u};
+        if (live) {
+          const int jf1 = (off - B0 + pg) >> 2;
+          const int nblk = ((((off + pg + 2) & ~3) + 4) - B0) >> 2;
+          int j = jf0 + fg;
+          for (; j + fG < jf1; j += 2 * fG) {
+            block_full(arr, B0 + 4 * j, pg, d);
+            block_full(arr, B0 + 4 * (j + fG), pg, e);
+          }
+          if (j < jf1) block_full(arr, B0 + 4 * j, pg, d);
+          for (int which = fg; which < 3; which += fG) {
+            const int je = which == 0 ? 0 : jf1 + which - 1;
+            if (which == 0 ? jf0 == 1 : je < nblk) block_edge(arr, B0 + 4 * je, pg, off, e);
+          }
+#pragma unroll
+          for (int l = 0; l < 4; l++) d[l] += e[l];
+        }
+        combine(d, fg, fG, fG);
+        if (live && fg == 0) fold(d, pg, lo, hi, bd, bp, wd, wp);
       }
     }
+    T_END(coarse ? 2 : 4);
+#ifdef K4_TIMING
+    const long long _t1 = clock64();
+#endif
     unsigned best_diff, worst_diff;
     int best, worst;
-    pick<true>(bd, bp, &best_diff, &best);
-    pick<false>(wd, wp, &worst_diff, &worst);
-    __syncwarp();  // acc[] is rewritten by the next search
+    pick2(bd, bp, wd, wp, &best_diff, &best, &worst_diff, &worst);
     // the C scan starts from (maxDiff = 0, worstPeriod = 255) and only replaces
     // it with a strictly larger ratio
     if (worst_diff == 0u) worst = 255;
-    *minDiff = (int)(best_diff / (unsigned)best);
-    *maxDiff = (int)(worst_diff / (unsigned)worst);
+    *minDiff = udiv_small(best_diff, best);
+    *maxDiff = udiv_small(worst_diff, worst);
+#ifdef K4_TIMING
+    if (lane == 0 && timing) atomicAdd(&g_k4_cycles[coarse ? 3 : 5], (unsigned long long)(clock64() - _t1 + (*minDiff & 0)));
+#endif
     return best;
   }
 
@@ -342,6 +472,9 @@ struct Sonic {
           position += newSamples;
         } else {
           ensure(pos, maxReq);
+#ifdef K4_TIMING
+          if (lane == 0 && timing) atomicAdd(&g_k4_cycles[9], 1ULL);
+#endif
           const int period = find_pitch_period(pos);
           if (speed > 1.0f) {
             if (speed >= 2.0f) {
@@ -389,26 +522,9 @@ struct Sonic {
   }
 };
 
-__host__ __device__ inline int k4_acc_entries(const Geometry& g) {
-  int coarse = g.max_period / g.skip - g.min_period / g.skip + 1;
-  int fine = g.skip != 1 ? 8 * g.skip + 1 : 0;
-  int n = (coarse > fine ? coarse : fine) + 8;
-  return (n + 3) & ~3;
-}
-
-// coarse work items: groups q = lo/4 .. hi/4, blocks 0 .. q (the last one masked)
-__host__ __device__ inline int k4_coarse_items(const Geometry& g) {
-  const int lo = g.min_period / g.skip, hi = g.max_period / g.skip;
-  int n = 0;
-  for (int q = lo >> 2; q <= (hi >> 2); q++) n += q + 1;
-  return n;
-}
-
 __host__ __device__ inline size_t k4_warp_smem(const Geometry& g, int buf_frames) {
   size_t b = (size_t)(buf_frames + kPad) * sizeof(int);
   b += (size_t)((g.max_required / g.skip + kPad + 3) & ~3) * sizeof(int);
-  b += (size_t)k4_acc_entries(g) * sizeof(unsigned);
-  b += (size_t)((k4_coarse_items(g) + 7) & ~7) * sizeof(unsigned short);
   if (g.channels > 1) b += (size_t)buf_frames * g.channels * sizeof(short);
   return (b + 15) & ~(size_t)15;
 }
@@ -425,6 +541,12 @@ __global__ void __launch_bounds__(WARPS * 32) k4_sonic(K4Params p) {
 
   Sonic k;
   k.lane = threadIdx.x & 31;
+#ifdef K4_TIMING
+  k.timing = (s == 0) && !p.flush;
+  const long long t_kernel = clock64();
+#else
+  k.timing = false;
+#endif
   k.C = g.channels;
   k.S = g.step;
   k.minP = g.min_period;
@@ -437,23 +559,39 @@ __global__ void __launch_bounds__(WARPS * 32) k4_sonic(K4Params p) {
   unsigned char* base = smem_raw + (size_t)warp * k4_warp_smem(g, p.buf_frames);
   k.w32 = reinterpret_cast<int*>(base);
   k.ds32 = k.w32 + k.bufN + kPad;
-  k.acc = reinterpret_cast<unsigned*>(k.ds32 + ((k.maxReq / k.skip + kPad + 3) & ~3));
-  k.items = reinterpret_cast<unsigned short*>(k.acc + k4_acc_entries(g));
-  k.n_items = k4_coarse_items(g);
-  k.buf = reinterpret_cast<short*>(k.items + ((k.n_items + 7) & ~7));
+  k.buf = reinterpret_cast<short*>(k.ds32 + ((k.maxReq / k.skip + kPad + 3) & ~3));
   k.bufStart = 0;
   k.bufLen = 0;
   k.dec_magic = (unsigned)((0x100000000ULL + (unsigned)(k.C * k.skip) - 1) / (unsigned)(k.C * k.skip));
   {
-    // coarse item list and fine-pass lane mapping (lags rounded out to fours)
+    // lane mappings (lags rounded out to groups of four)
     const int c_lo = k.minP / k.skip, c_hi = k.maxP / k.skip;
-    if (k.lane == 0) {
-      int w = 0;
-      for (int q = c_lo >> 2; q <= (c_hi >> 2); q++) {
-        for (int j = 0; j <= q; j++) k.items[w++] = (unsigned short)(((q - (c_lo >> 2)) << 8) | j);
-      }
+    const int qlo = c_lo >> 2, qhi = c_hi >> 2;
+    // coarse: group q has q + 1 blocks; give every group ceil((q + 1) / T) adjacent
+    // lanes with the smallest T that fits the warp
+    int T = 1;
+    for (;; T++) {
+      int sum = 0;
+      for (int q = qlo; q <= qhi; q++) sum += (q + T) / T;
+      if (sum <= 32) break;
     }
-    const int fine_groups = k.skip != 1 ? 2 * k.skip + 2 : (c_hi >> 2) - (c_lo >> 2) + 1;
+    k.cGi = -1;
+    k.cSub = 0;
+    k.cG = 1;
+    k.cMaxG = 1;
+    int first = 0;
+    for (int q = qlo; q <= qhi; q++) {
+      const int n = (q + T) / T;
+      if (k.lane >= first && k.lane < first + n) {
+        k.cGi = q - qlo;
+        k.cSub = k.lane - first;
+        k.cG = n;
+      }
+      if (n > k.cMaxG) k.cMaxG = n;
+      first += n;
+    }
+    // fine (and single-stage) pass: fG adjacent lanes per group
+    const int fine_groups = k.skip != 1 ? 2 * k.skip + 2 : qhi - qlo + 1;
     k.fG = 32 / fine_groups;
     if (k.fG < 1) k.fG = 1;
     k.fPerRound = 32 / k.fG;
@@ -552,6 +690,12 @@ __global__ void __launch_bounds__(WARPS * 32) k4_sonic(K4Params p) {
     }
   }
 
+#ifdef K4_TIMING
+  if (k.lane == 0 && k.timing) {
+    atomicAdd(&g_k4_cycles[8], (unsigned long long)(clock64() - t_kernel));
+    atomicAdd(&g_k4_cycles[10], (unsigned long long)n_events);
+  }
+#endif
   if (k.lane == 0) {
     p.st.sonic_head[s] = k.head;
     p.st.sonic_fed[s] = k.fed;
@@ -588,6 +732,18 @@ static cudaError_t launch_k4_t(K4Params& p, cudaStream_t stream) {
   count_launch();
   return cudaGetLastError();
 }
+
+#ifdef K4_TIMING
+extern "C" int speedyDebugK4Cycles(unsigned long long* out16, int reset) {
+  cudaDeviceSynchronize();
+  if (out16) cudaMemcpyFromSymbol(out16, g_k4_cycles, sizeof(unsigned long long) * 16);
+  if (reset) {
+    unsigned long long z[16] = {0};
+    cudaMemcpyToSymbol(g_k4_cycles, z, sizeof(z));
+  }
+  return 1;
+}
+#endif
 
 cudaError_t launch_k4(const K4Params& p0, cudaStream_t stream) {
   K4Params p = p0;

@@ -337,3 +337,17 @@ def test_process_host_api_matches_device_path():
     assert np.array_equal(cnt_a, cnt_b)
     for s in range(n):
         assert np.array_equal(out_a[s, :cnt_a[s]], out_b[s, :cnt_b[s]]), s
+    # pinned host buffers take the zero-copy output path (kernel stores into host memory)
+    h_in = torch.from_numpy(pcm).pin_memory()
+    h_out = torch.zeros((n, cap, 1), dtype=torch.int16).pin_memory()
+    h_cnt = torch.zeros(n, dtype=torch.int32)
+    b = sb.Batch(n, rate, 1, speed=2.5, nonlinear=1.0, feedback=0.1, max_write_frames=frames, out_capacity=cap)
+    for _ in range(2):
+        h_out.zero_()
+        b.process_ptr(h_in, frames, h_out, cap, h_cnt)
+        assert np.array_equal(h_cnt.numpy(), cnt_b)
+        got = h_out.numpy()
+        for s in range(n):
+            assert np.array_equal(got[s, :cnt_b[s]], out_b[s, :cnt_b[s]]), s
+            assert not got[s, cnt_b[s]:].any()
+    b.close()
