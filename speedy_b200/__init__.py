@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libspeedy_b200.so")
+LIB_PATH = os.environ.get("SPEEDY_B200_LIB") or os.path.join(HERE, "libspeedy_b200.so")
 
 TAP_TENSION, TAP_SPEED, TAP_FEATURES, TAP_SPECTROGRAM, TAP_ENERGY = 1, 2, 4, 8, 16
 STATUS_OUTPUT_OVERFLOW, STATUS_FLUSHED, STATUS_INPUT_OVERFLOW, STATUS_READ_TRUNCATED = 1, 2, 4, 8

@@ -295,26 +295,49 @@ __global__ void __launch_bounds__(WARPS * 32) k1_spectral_480(K1Params p) {
       float* tap = nullptr;
       if (p.tap_spec && k >= k0 && k < k1) tap = p.tap_spec + ((size_t)s * p.tap_stride + (k - kA)) * 480;
       float e = 0.0f, mx = 0.0f;
-      for (int kb = lane; kb < H16; kb += 32) {
-        float2 zk = Z[kb];
-        float2 zm = Z[kb == 0 ? 0 : 240 - kb];
-        float2 zc = make_float2(zm.x, -zm.y);
-        float2 sum = cscale(cadd(zk, zc), 0.5f);
-        float2 dif = cscale(csub(zk, zc), 0.5f);
-        float2 wd = mul_mi(cmul(s_tw480[kb], dif));
-        float re = sum.x + wd.x, im = sum.y + wd.y;
+      // Real-FFT split, two bins per step.  With S = (Z[t] + conj Z[240-t]) / 2,
+      // D = (Z[t] - conj Z[240-t]) / 2 and P = W_480^t D:
+      //   X[t] = S - i P,   X[240-t] = conj(S) - i conj(P)      (W_480^(240-t) = -conj W_480^t)
+      for (int t = 1 + lane; t < 120; t += 32) {
+        const float2 zk = Z[t], zm = Z[240 - t];
+        const float sx = 0.5f * (zk.x + zm.x), sy = 0.5f * (zk.y - zm.y);
+        const float dx = 0.5f * (zk.x - zm.x), dy = 0.5f * (zk.y + zm.y);
+        const float2 w = s_tw480[t];
+        const float px = w.x * dx - w.y * dy, py = w.x * dy + w.y * dx;
+        const float re0 = sx + py, im0 = sy - px;    // X[t]
+        const float re1 = sx - py, im1 = sy + px;    // X[240-t] up to the sign of im
         // speedy.c:434-436 squares and sums in float; so does this
-        const float pw = __fadd_rn(__fmul_rn(re, re), __fmul_rn(im, im));
-        lmag[kb] = __log2f(pw);
-        if (kb >= 1) {
-          e += pw;
-          mx = fmaxf(mx, pw);
-        }
+        const float p0 = __fadd_rn(__fmul_rn(re0, re0), __fmul_rn(im0, im0));
+        const float p1 = __fadd_rn(__fmul_rn(re1, re1), __fmul_rn(im1, im1));
+        lmag[t] = __log2f(p0);
+        lmag[240 - t] = __log2f(p1);
+        e += p0 + p1;
+        mx = fmaxf(mx, fmaxf(p0, p1));
         if (tap) {
-          const float m = __fsqrt_rn(pw);
-          tap[kb] = m;
-          if (kb >= 1) tap[480 - kb] = m;
-          if (kb == 0) tap[240] = fabsf(zk.x - zk.y);  // X[N/2] = Re(Z0) - Im(Z0)
+          const float m0 = __fsqrt_rn(p0), m1 = __fsqrt_rn(p1);
+          tap[t] = m0;
+          tap[480 - t] = m0;
+          tap[240 - t] = m1;
+          tap[240 + t] = m1;
+        }
+      }
+      if (lane == 0) {
+        // bins 0, N/4 and N/2: X[0] = Re Z0 + Im Z0, X[N/2] = Re Z0 - Im Z0,
+        // X[120] = conj(Z[120]) (W_480^120 = -i)
+        const float2 z0 = Z[0], zq = Z[120];
+        const float x0 = z0.x + z0.y;
+        const float p0 = __fmul_rn(x0, x0);
+        const float pq = __fadd_rn(__fmul_rn(zq.x, zq.x), __fmul_rn(zq.y, zq.y));
+        lmag[0] = __log2f(p0);
+        lmag[120] = __log2f(pq);
+        e += pq;
+        mx = fmaxf(mx, pq);
+        if (tap) {
+          tap[0] = fabsf(x0);
+          tap[240] = fabsf(z0.x - z0.y);
+          const float mq = __fsqrt_rn(pq);
+          tap[120] = mq;
+          tap[360] = mq;
         }
       }
       e_slot[slot] = warp_sum(e);

@@ -1,5 +1,5 @@
 // K4 — Sonic time-scale modification: AMDF pitch-period search and
-// pitch-synchronous overlap-add, one warp per stream.
+// pitch-synchronous overlap-add, one CTA of NW warps per stream (NW = 1, 2 or 4).
 //
 // Replaces what the reference does through upstream Sonic
 // (soniclib.c:354, 369-370, 398, 547, 551 -> sonicIntSetSpeed,
@@ -16,12 +16,15 @@
 // associative, so splitting the AMDF sums across lanes cannot change a result:
 // given identical per-frame speeds the output is bit-exact.
 //
-// Why one warp per stream.  The splice cursor is strictly sequential (the next
-// position depends on the period just found), so a stream is a chain of ~80 pitch
-// iterations per second of audio; parallelism comes from the streams.  A warp
-// needs no block barrier, no cross-warp reduction and executes the uniform
-// bookkeeping once instead of once per warp; the profile of the earlier
-// multi-warp version was dominated by exactly that overhead.
+// Warps per stream.  The splice cursor is strictly sequential (the next position
+// depends on the period just found), so a stream is a chain of ~80 pitch iterations
+// per second of audio and parallelism comes from the streams.  With thousands of
+// streams per GPU one warp per stream is the efficient shape: no block barrier, the
+// uniform bookkeeping executed once.  With few streams (the 1024-stream benchmark
+// leaves 7 per SM) the chain's latency is what is measured, and 2 or 4 warps share
+// the parallel loops of a stream (window refill, decimation, AMDF blocks, overlap-
+// add); all warps run the same uniform control flow on replicated scalar state and
+// meet at three barriers per pitch iteration.
 //
 // Sonic's input FIFO is never materialised: the stream keeps two absolute
 // cursors (head = first unconsumed frame, fed = one past the last frame handed
@@ -48,7 +51,7 @@ namespace {
 #ifdef K4_TIMING
 __device__ unsigned long long g_k4_cycles[16];
 #define T_BEGIN() const long long _t0 = clock64()
-#define T_END(slot) do { if (lane == 0 && timing) atomicAdd(&g_k4_cycles[slot], (unsigned long long)(clock64() - _t0)); } while (0)
+#define T_END(slot) do { if (vl == 0 && timing) atomicAdd(&g_k4_cycles[slot], (unsigned long long)(clock64() - _t0)); } while (0)
 #else
 #define T_BEGIN() do {} while (0)
 #define T_END(slot) do {} while (0)
@@ -56,8 +59,11 @@ __device__ unsigned long long g_k4_cycles[16];
 
 constexpr int kPad = 32;  // over-read slack behind the window and the decimated copy
 constexpr unsigned kFull = 0xffffffffu;
+constexpr int kMaxGroups = 64;  // lag groups of four per search (>= 2 * skip + 2)
 
+template <int NW>
 struct Sonic {
+  static constexpr int VL = 32 * NW;  // lanes cooperating on one stream
   // geometry
   int C, S, minP, maxP, maxReq, skip;
   long long cap;
@@ -76,7 +82,9 @@ struct Sonic {
   long long head, fed, outTotal;
   int prevPeriod, prevMinDiff, remCopy, outCount, status;
   short* out;
-  int lane;
+  int lane, warp, vl;
+  unsigned* sums;  // [2][4 * kMaxGroups] per-lag totals handed from the group leaders to every warp
+  int parity;
   // fine-pass lane mapping: fG sub-lanes per lag group
   int fG, fPerRound, fGi0, fg;
   // coarse-pass lane mapping: group cGi (-1 = idle), sub-lane cSub of cG, largest cG
@@ -85,14 +93,18 @@ struct Sonic {
   bool timing;
 
   // Make [start, start + count) resident in the shared window (count <= bufN - 8).
+  __device__ __forceinline__ void sync() {
+    if (NW == 1) __syncwarp(); else __syncthreads();
+  }
+
   __device__ __forceinline__ void ensure(long long start, int count) {
     if (start >= bufStart && start + count <= bufStart + bufLen) return;
     T_BEGIN();
-    __syncwarp();  // every lane is done with the old window
+    sync();  // every lane is done with the old window
     bufStart = start & ~7LL;  // keeps the 16-byte loads of the refill aligned
     bufLen = bufN;
-    stage_mono<32, int>(src, bufStart, bufN, zero_from, w32, C > 1 ? buf : nullptr, lane);
-    __syncwarp();
+    stage_mono<VL, int>(src, bufStart, bufN, zero_from, w32, C > 1 ? buf : nullptr, vl);
+    sync();
     T_END(0);
   }
 
@@ -115,12 +127,12 @@ struct Sonic {
     short* o = out + base;
     T_BEGIN();
     if (C == 1) {
-      for (int i = lane; i < total; i += 32) {
+      for (int i = vl; i < total; i += VL) {
         if (i < room) o[i] = (short)w32[o0 + i];
       }
     } else {
       const short* p = buf + (size_t)o0 * C;
-      for (int i = lane; i < total; i += 32) {
+      for (int i = vl; i < total; i += VL) {
         if (i < room) o[i] = p[i];
       }
     }
@@ -151,14 +163,14 @@ struct Sonic {
     T_BEGIN();
     const float rcp_n = __frcp_rn((float)(n > 0 ? n : 1));
     if (C == 1) {
-      for (int t = lane; t < total; t += 32) {
+      for (int t = vl; t < total; t += VL) {
         int v = div_trunc(w32[d0 + t] * (n - t) + w32[u0 + t] * t, n, rcp_n);
         if (t < room) o[t] = (short)v;
       }
     } else {
       const short* dp = buf + (size_t)d0 * C;
       const short* up_ = buf + (size_t)u0 * C;
-      for (int i = lane; i < total; i += 32) {
+      for (int i = vl; i < total; i += VL) {
         int t = i / C;
         int v = div_trunc((int)dp[i] * (n - t) + (int)up_[i] * t, n, rcp_n);
         if (i < room) o[i] = (short)v;
@@ -174,32 +186,8 @@ struct Sonic {
     T_BEGIN();
     const int count = maxReq / skip;
     const int per = C * skip;
-    if (C == 1 && (skip == 2 || skip == 4 || skip == 8)) {
-      // conflict-free rows of 32 consecutive samples; the `skip`-sums are segmented
-      // sums over adjacent lanes, left in the first lane of every segment
-      const int rows = (count * skip + 31) >> 5;
-      for (int r0 = 0; r0 < rows; r0 += 4) {
-        int v[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) {  // four independent rows in flight
-          // (reads past the last frame land in the pad: those sums are not stored)
-          v[u] = r0 + u < rows ? w32[off + 32 * (r0 + u) + lane] : 0;
-        }
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-          v[u] += __shfl_down_sync(kFull, v[u], 1);
-          if (skip >= 4) v[u] += __shfl_down_sync(kFull, v[u], 2);
-          if (skip >= 8) v[u] += __shfl_down_sync(kFull, v[u], 4);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-          const int i = (32 * (r0 + u) + lane) >> (skip == 2 ? 1 : (skip == 4 ? 2 : 3));
-          const int qa = (int)__umulhi((unsigned)abs(v[u]), dec_magic);
-          if ((lane & (skip - 1)) == 0 && i < count) ds32[i] = v[u] < 0 ? -qa : qa;
-        }
-      }
-    } else {
-      for (int i = lane; i < count; i += 32) {
+    {
+      for (int i = vl; i < count; i += VL) {
         int v = 0;
         if (C == 1) {
           const int* q = w32 + off + i * skip;
@@ -216,7 +204,7 @@ struct Sonic {
         ds32[i] = v < 0 ? -qa : qa;
       }
     }
-    __syncwarp();
+    sync();
     T_END(1);
   }
 
@@ -327,7 +315,8 @@ struct Sonic {
     }
   }
 
-  // Sum the partial lag sums of the `G` adjacent lanes of a group into its first lane.
+  // Sum the partial lag sums of the `G` adjacent lanes of a group (all in one warp)
+  // into its first lane.
   __device__ __forceinline__ void combine(unsigned (&d)[4], int sub, int G, int maxG) {
     for (int delta = 1; delta < maxG; delta <<= 1) {
 #pragma unroll
@@ -344,9 +333,11 @@ struct Sonic {
                                         int* maxDiff) {
     const int g0 = lo >> 2;  // first lag group (lags 4*g0 .. 4*g0+3)
     const int ngroups = (hi >> 2) - g0 + 1;
-    T_BEGIN();
+    unsigned* tot = sums + parity * (4 * kMaxGroups);
+    parity ^= 1;
     unsigned bd = 0, wd = 0;
     int bp = 0, wp = 0;
+    T_BEGIN();
     if (coarse) {
       // off == 0 and the lag range is fixed: a static lane assignment with more
       // lanes for the longer lags; group q has q fully valid blocks (j < q) and one
@@ -366,16 +357,18 @@ struct Sonic {
         for (int l = 0; l < 4; l++) d[l] += e[l];
       }
       combine(d, cSub, cG, cMaxG);
-      if (cGi >= 0 && cSub == 0) fold(d, pg, lo, hi, bd, bp, wd, wp);
+      if (cGi >= 0 && cSub == 0) {
+        if (NW == 1) fold(d, pg, lo, hi, bd, bp, wd, wp);
+        else *reinterpret_cast<uint4*>(tot + 4 * cGi) = make_uint4(d[0], d[1], d[2], d[3]);
+      }
     } else {
       // blocks of group gi: j = 0 .. nblk-1 at B0 + 4j; fully valid for jf0 <= j < jf1,
       // the head block (j = 0 when off is unaligned) and one or two tail blocks are
       // handled by the group's sub-lanes under a per-element mask
       const int B0 = off & ~3;
       const int jf0 = (off & 3) ? 1 : 0;
-      const int rounds = (ngroups + fPerRound - 1) / fPerRound;
-      for (int round = 0; round < rounds; round++) {
-        const int gi = fGi0 + round * fPerRound;
+      for (int gbase = 0; gbase < ngroups; gbase += fPerRound) {
+        const int gi = fGi0 + gbase;
         const bool live = gi < ngroups;  // also false for idle lanes
         const int pg = 4 * (g0 + gi);
         unsigned d[4] = {0u, 0u, 0u, 0u}, e[4] = {0u, 0u, 0u, 0u};
@@ -396,13 +389,28 @@ struct Sonic {
           for (int l = 0; l < 4; l++) d[l] += e[l];
         }
         combine(d, fg, fG, fG);
-        if (live && fg == 0) fold(d, pg, lo, hi, bd, bp, wd, wp);
+        if (live && fg == 0) {
+          // (one warp: rounds ascend, so the running candidates see ascending lags)
+          if (NW == 1) fold(d, pg, lo, hi, bd, bp, wd, wp);
+          else *reinterpret_cast<uint4*>(tot + 4 * gi) = make_uint4(d[0], d[1], d[2], d[3]);
+        }
       }
     }
     T_END(coarse ? 2 : 4);
 #ifdef K4_TIMING
     const long long _t1 = clock64();
 #endif
+    if (NW > 1) {
+      // every warp folds all groups (ascending lags per lane) and picks: the result
+      // is identical in all warps, no broadcast needed.  The totals are double-
+      // buffered, so the next search may start writing while a slower warp reads.
+      sync();
+      for (int gi = lane; gi < ngroups; gi += 32) {
+        const uint4 t4 = *reinterpret_cast<const uint4*>(tot + 4 * gi);
+        const unsigned d[4] = {t4.x, t4.y, t4.z, t4.w};
+        fold(d, 4 * (g0 + gi), lo, hi, bd, bp, wd, wp);
+      }
+    }
     unsigned best_diff, worst_diff;
     int best, worst;
     pick2(bd, bp, wd, wp, &best_diff, &best, &worst_diff, &worst);
@@ -412,7 +420,7 @@ struct Sonic {
     *minDiff = udiv_small(best_diff, best);
     *maxDiff = udiv_small(worst_diff, worst);
 #ifdef K4_TIMING
-    if (lane == 0 && timing) atomicAdd(&g_k4_cycles[coarse ? 3 : 5], (unsigned long long)(clock64() - _t1 + (*minDiff & 0)));
+    if (vl == 0 && timing) atomicAdd(&g_k4_cycles[coarse ? 3 : 5], (unsigned long long)(clock64() - _t1 + (*minDiff & 0)));
 #endif
     return best;
   }
@@ -473,7 +481,7 @@ struct Sonic {
         } else {
           ensure(pos, maxReq);
 #ifdef K4_TIMING
-          if (lane == 0 && timing) atomicAdd(&g_k4_cycles[9], 1ULL);
+          if (vl == 0 && timing) atomicAdd(&g_k4_cycles[9], 1ULL);
 #endif
           const int period = find_pitch_period(pos);
           if (speed > 1.0f) {
@@ -522,25 +530,31 @@ struct Sonic {
   }
 };
 
-__host__ __device__ inline size_t k4_warp_smem(const Geometry& g, int buf_frames) {
+__host__ __device__ inline size_t k4_stream_smem(const Geometry& g, int buf_frames) {
   size_t b = (size_t)(buf_frames + kPad) * sizeof(int);
   b += (size_t)((g.max_required / g.skip + kPad + 3) & ~3) * sizeof(int);
+  b += (size_t)2 * 4 * kMaxGroups * sizeof(unsigned);
   if (g.channels > 1) b += (size_t)buf_frames * g.channels * sizeof(short);
   return (b + 15) & ~(size_t)15;
 }
 
 }  // namespace
 
-template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) k4_sonic(K4Params p) {
+// MINB: resident CTAs per SM the register allocation is held to (1 = unconstrained).
+// Few streams: registers are free, latency is what counts.  Many streams: 16 resident
+// warps per SM hide the chain's latency, worth a tighter allocation.
+template <int NW, int MINB>
+__global__ void __launch_bounds__(NW * 32, MINB) k4_sonic(K4Params p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int warp = threadIdx.x >> 5;
-  const int s = blockIdx.x * WARPS + warp;
+  const int s = blockIdx.x;
   if (s >= p.n_streams) return;
   const Geometry& g = p.g;
 
-  Sonic k;
+  Sonic<NW> k;
   k.lane = threadIdx.x & 31;
+  k.warp = threadIdx.x >> 5;
+  k.vl = threadIdx.x;
+  k.parity = 0;
 #ifdef K4_TIMING
   k.timing = (s == 0) && !p.flush;
   const long long t_kernel = clock64();
@@ -555,11 +569,11 @@ __global__ void __launch_bounds__(WARPS * 32) k4_sonic(K4Params p) {
   k.skip = g.skip;
   k.cap = p.out_capacity;
   k.bufN = p.buf_frames;
-  // carve-up of this warp's slice (every piece a multiple of 16 bytes)
-  unsigned char* base = smem_raw + (size_t)warp * k4_warp_smem(g, p.buf_frames);
-  k.w32 = reinterpret_cast<int*>(base);
+  // carve-up (every piece a multiple of 16 bytes)
+  k.w32 = reinterpret_cast<int*>(smem_raw);
   k.ds32 = k.w32 + k.bufN + kPad;
-  k.buf = reinterpret_cast<short*>(k.ds32 + ((k.maxReq / k.skip + kPad + 3) & ~3));
+  k.sums = reinterpret_cast<unsigned*>(k.ds32 + ((k.maxReq / k.skip + kPad + 3) & ~3));
+  k.buf = reinterpret_cast<short*>(k.sums + 2 * 4 * kMaxGroups);
   k.bufStart = 0;
   k.bufLen = 0;
   k.dec_magic = (unsigned)((0x100000000ULL + (unsigned)(k.C * k.skip) - 1) / (unsigned)(k.C * k.skip));
@@ -567,12 +581,28 @@ __global__ void __launch_bounds__(WARPS * 32) k4_sonic(K4Params p) {
     // lane mappings (lags rounded out to groups of four)
     const int c_lo = k.minP / k.skip, c_hi = k.maxP / k.skip;
     const int qlo = c_lo >> 2, qhi = c_hi >> 2;
-    // coarse: group q has q + 1 blocks; give every group ceil((q + 1) / T) adjacent
-    // lanes with the smallest T that fits the warp
+    // coarse: group q has q + 1 blocks.  Groups are dealt to the warps largest first
+    // (least-loaded warp takes the next one); inside a warp every group gets
+    // ceil((q + 1) / T) adjacent lanes with the smallest T that fits 32 lanes.
+    int load[NW];
+    int owner[kMaxGroups];
+#pragma unroll
+    for (int w = 0; w < NW; w++) load[w] = 0;
+    for (int q = qhi; q >= qlo; q--) {
+      int best_w = 0;
+#pragma unroll
+      for (int w = 1; w < NW; w++) {
+        if (load[w] < load[best_w]) best_w = w;
+      }
+      owner[q - qlo] = best_w;
+      load[best_w] += q + 1;
+    }
     int T = 1;
     for (;; T++) {
       int sum = 0;
-      for (int q = qlo; q <= qhi; q++) sum += (q + T) / T;
+      for (int q = qlo; q <= qhi; q++) {
+        if (owner[q - qlo] == k.warp) sum += (q + T) / T;
+      }
       if (sum <= 32) break;
     }
     k.cGi = -1;
@@ -581,6 +611,7 @@ __global__ void __launch_bounds__(WARPS * 32) k4_sonic(K4Params p) {
     k.cMaxG = 1;
     int first = 0;
     for (int q = qlo; q <= qhi; q++) {
+      if (owner[q - qlo] != k.warp) continue;
       const int n = (q + T) / T;
       if (k.lane >= first && k.lane < first + n) {
         k.cGi = q - qlo;
@@ -590,20 +621,22 @@ __global__ void __launch_bounds__(WARPS * 32) k4_sonic(K4Params p) {
       if (n > k.cMaxG) k.cMaxG = n;
       first += n;
     }
-    // fine (and single-stage) pass: fG adjacent lanes per group
+    // fine (and single-stage) pass: fG adjacent lanes per group, groups never
+    // straddle a warp: the largest fG with NW * (32 / fG) >= the group count
     const int fine_groups = k.skip != 1 ? 2 * k.skip + 2 : qhi - qlo + 1;
-    k.fG = 32 / fine_groups;
-    if (k.fG < 1) k.fG = 1;
-    k.fPerRound = 32 / k.fG;
-    k.fGi0 = k.lane / k.fG;
-    k.fg = k.lane - k.fGi0 * k.fG;
-    if (k.lane >= k.fPerRound * k.fG) k.fGi0 = 1 << 30;  // idle lane
+    k.fG = 32;
+    while (k.fG > 1 && NW * (32 / k.fG) < fine_groups) k.fG--;
+    const int gpw = 32 / k.fG;  // groups per warp
+    k.fPerRound = NW * gpw;
+    const int slot = k.lane / k.fG;
+    k.fg = k.lane - slot * k.fG;
+    k.fGi0 = slot < gpw ? k.warp * gpw + slot : (1 << 30);  // idle lanes never match
   }
-  for (int i = k.lane; i < kPad; i += 32) {  // the over-read pads
+  for (int i = k.vl; i < kPad; i += Sonic<NW>::VL) {  // the over-read pads
     k.w32[k.bufN + i] = 0;
     k.ds32[k.maxReq / k.skip + i] = 0;
   }
-  __syncwarp();
+  k.sync();
 
   const long long t_old = p.st.total[s];
   const long long t_new = p.flush ? t_old : t_old + (p.counts ? p.counts[s] : p.frames);
@@ -691,12 +724,12 @@ __global__ void __launch_bounds__(WARPS * 32) k4_sonic(K4Params p) {
   }
 
 #ifdef K4_TIMING
-  if (k.lane == 0 && k.timing) {
+  if (k.vl == 0 && k.timing) {
     atomicAdd(&g_k4_cycles[8], (unsigned long long)(clock64() - t_kernel));
     atomicAdd(&g_k4_cycles[10], (unsigned long long)n_events);
   }
 #endif
-  if (k.lane == 0) {
+  if (k.vl == 0) {
     p.st.sonic_head[s] = k.head;
     p.st.sonic_fed[s] = k.fed;
     p.st.out_total[s] = k.outTotal;
@@ -718,38 +751,33 @@ static int k4_buf_frames(const Geometry& g, int n_streams) {
   return (n + 63) & ~63;
 }
 
-template <int WARPS>
+template <int NW, int MINB>
 static cudaError_t launch_k4_t(K4Params& p, cudaStream_t stream) {
-  const size_t smem = (size_t)WARPS * k4_warp_smem(p.g, p.buf_frames);
+  const size_t smem = k4_stream_smem(p.g, p.buf_frames);
   static size_t attr = 0;
   if (smem > attr) {
-    cudaError_t e = cudaFuncSetAttribute(k4_sonic<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k4_sonic<NW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     attr = smem;
   }
-  const int blocks = (p.n_streams + WARPS - 1) / WARPS;
-  k4_sonic<WARPS><<<blocks, WARPS * 32, smem, stream>>>(p);
+  k4_sonic<NW, MINB><<<p.n_streams, NW * 32, smem, stream>>>(p);
   count_launch();
   return cudaGetLastError();
 }
 
-#ifdef K4_TIMING
-extern "C" int speedyDebugK4Cycles(unsigned long long* out16, int reset) {
-  cudaDeviceSynchronize();
-  if (out16) cudaMemcpyFromSymbol(out16, g_k4_cycles, sizeof(unsigned long long) * 16);
-  if (reset) {
-    unsigned long long z[16] = {0};
-    cudaMemcpyToSymbol(g_k4_cycles, z, sizeof(z));
-  }
-  return 1;
-}
-#endif
-
 cudaError_t launch_k4(const K4Params& p0, cudaStream_t stream) {
   K4Params p = p0;
   p.buf_frames = k4_buf_frames(p.g, p.n_streams);
-  // one warp per stream; CTAs of one warp keep the grid fine-grained
-  return launch_k4_t<1>(p, stream);
+  // threads per stream: with few streams per SM the serial splice chain is latency
+  // bound and extra warps shorten it; with many streams one warp each is the most
+  // work-efficient shape
+  int t = p.threads_per_stream;
+  if (t == 0) t = 32;  // measured: extra warps do not shorten the chain enough to pay for their barriers
+  if (t <= 32) {
+    return p.n_streams > 148 * 12 ? launch_k4_t<1, 16>(p, stream) : launch_k4_t<1, 1>(p, stream);
+  }
+  if (t <= 64) return launch_k4_t<2, 1>(p, stream);
+  return launch_k4_t<4, 1>(p, stream);
 }
 
 }  // namespace speedy
