@@ -11,6 +11,7 @@
 #include <atomic>
 #include <mutex>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/speedy_b200.h"
@@ -18,6 +19,8 @@
 #include "synth.h"
 
 namespace speedy {
+
+constexpr int kPipeEvents = 16;
 
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
@@ -255,16 +258,18 @@ struct speedyBatchStruct {
   int32_t* d_counts_stage;
   int32_t* h_pinned_counts;
   // speedyBatchProcess: double-buffered input chunks and the copy streams
-  int16_t* d_pipe[3];
-  long long pipe_chunk;
   int pipe_ready;
   cudaStream_t s_h2d, s_d2h;
   int* d_snap[3];       // out_count snapshots per chunk
   int* d_done;          // frames already delivered to the host
-  // per-kernel timing (speedyBatchSetProfiling)
+  // per-kernel timing (speedyBatchSetProfiling): (start, stop) event pairs
   int profiling;
-  cudaEvent_t ev[6];
-  int ev_recorded;   // 0 none, 1 write, 2 flush
+  std::vector<cudaEvent_t> prof_events;
+  std::vector<std::pair<int, int>> prof_marks;  // (slot, is_begin), parallel to the events in use
+  int prof_used;
+  // internal stream the resynthesis kernel runs on when a write is split, fork/join events
+  cudaStream_t s_sonic;
+  cudaEvent_t ev_pipe[16];
 };
 
 namespace {
@@ -369,7 +374,9 @@ void speedyBatchDestroy(speedyBatch b) {
   if (b->s_d2h) cudaStreamDestroy(b->s_d2h);
   for (void* p : b->allocs) cudaFree(p);
   if (b->h_pinned_counts) cudaFreeHost(b->h_pinned_counts);
-  for (int i = 0; i < 6; i++) if (b->ev[i]) cudaEventDestroy(b->ev[i]);
+  for (cudaEvent_t e : b->prof_events) cudaEventDestroy(e);
+  for (int i = 0; i < kPipeEvents; i++) if (b->ev_pipe[i]) cudaEventDestroy(b->ev_pipe[i]);
+  if (b->s_sonic) cudaStreamDestroy(b->s_sonic);
   if (b->own_stream) cudaStreamDestroy(b->own_stream);
   delete b;
 }
@@ -399,15 +406,14 @@ speedyBatch speedyBatchCreate(const speedyBatchConfig* cfg) {
   b->d_counts_stage = nullptr;
   b->d_override = nullptr;
   b->override_stride = 0;
-  b->d_pipe[0] = b->d_pipe[1] = b->d_pipe[2] = nullptr;
-  b->pipe_chunk = 0;
   b->pipe_ready = 0;
   b->s_h2d = b->s_d2h = nullptr;
   b->d_snap[0] = b->d_snap[1] = b->d_snap[2] = nullptr;
   b->d_done = nullptr;
   b->profiling = 0;
-  b->ev_recorded = 0;
-  for (int i = 0; i < 6; i++) b->ev[i] = nullptr;
+  b->prof_used = 0;
+  b->s_sonic = nullptr;
+  for (int i = 0; i < kPipeEvents; i++) b->ev_pipe[i] = nullptr;
   b->d_tap_spec = b->d_tap_energy = b->d_tap_features = b->d_tap_tension = b->d_tap_speed = nullptr;
   make_geometry(cfg->sample_rate, cfg->num_channels, cfg->match_matlab, &b->g);
   const Geometry& g = b->g;
@@ -548,18 +554,35 @@ int speedyBatchOverrideSpeeds(speedyBatch b, const float* speeds, int64_t frames
   return 1;
 }
 
-int speedyBatchWriteDevice(speedyBatch b, const int16_t* d_in, int64_t stride_frames, int64_t frames,
-                           const int32_t* d_counts, void* cuda_stream) {
-  if (!b) return 0;
-  if (frames < 0 || frames > b->cfg.max_write_frames) {
-    set_error("speedyBatchWriteDevice: frames exceeds max_write_frames");
-    return 0;
-  }
-  if (frames == 0) return 1;
-  CU_TRY(cudaSetDevice(b->cfg.device));
-  cudaStream_t st = pick_stream(b, cuda_stream);
-  const Geometry& g = b->g;
+// ---- one write, possibly as several launches over growing prefixes ----------
+namespace {
 
+struct WriteCall {
+  speedyBatch b;
+  const int16_t* d_in;
+  long long stride_frames, frames;
+  const int32_t* d_counts;
+};
+
+// per-kernel timing: accumulate event pairs (start, stop, slot) while profiling
+void prof_mark(speedyBatch b, cudaStream_t st, int slot, bool begin) {
+  if (!b->profiling) return;
+  cudaEvent_t e = nullptr;
+  if (b->prof_used < (int)b->prof_events.size()) {
+    e = b->prof_events[b->prof_used];
+  } else {
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    b->prof_events.push_back(e);
+  }
+  b->prof_used++;
+  cudaEventRecord(e, st);
+  b->prof_marks.push_back({slot, begin ? 1 : 0});
+}
+
+// analysis (K1 + K2) of the prefix (done, prefix] on stream sa
+int launch_analysis(const WriteCall& w, long long done, long long prefix, cudaStream_t sa) {
+  speedyBatch b = w.b;
+  const Geometry& g = b->g;
   K1Params k1;
   memset(&k1, 0, sizeof(k1));
   k1.g = g;
@@ -567,14 +590,15 @@ int speedyBatchWriteDevice(speedyBatch b, const int16_t* d_in, int64_t stride_fr
   k1.n_streams = b->n;
   k1.hist = b->d_hist[b->hist_cur];
   k1.hist_stride = b->hist_stride;
-  k1.in = d_in;
-  k1.in_stride_frames = stride_frames;
-  k1.counts = d_counts;
-  k1.frames = frames;
+  k1.in = w.d_in;
+  k1.in_stride_frames = w.stride_frames;
+  k1.counts = w.d_counts;
+  k1.frames = prefix;
+  k1.done = done;
   k1.feat = b->d_feat;
   k1.feat_stride = b->max_new_frames;
-  // at most this many analysis windows can complete in one write
-  k1.max_new_frames = (int)(frames / g.step) + 2;
+  // at most this many analysis windows can complete in this launch
+  k1.max_new_frames = (int)((prefix - done) / g.step) + 2;
   if (k1.max_new_frames > b->max_new_frames) k1.max_new_frames = b->max_new_frames;
   k1.window = b->d_window;
   k1.tw_n = b->d_tw_n;
@@ -583,17 +607,18 @@ int speedyBatchWriteDevice(speedyBatch b, const int16_t* d_in, int64_t stride_fr
   memcpy(k1.factors, b->factors, sizeof(k1.factors));
   k1.tap_spec = b->d_tap_spec;
   k1.tap_stride = b->max_new_frames;
-  if (b->profiling) CU_TRY(cudaEventRecord(b->ev[0], st));
-  CU_TRY(launch_k1(k1, st));  // streams with nonlinear factor 0 skip themselves
-  if (b->profiling) CU_TRY(cudaEventRecord(b->ev[1], st));
+  prof_mark(b, sa, 0, true);
+  CU_TRY(launch_k1(k1, sa));  // streams with nonlinear factor 0 skip themselves
+  prof_mark(b, sa, 0, false);
 
   K2Params k2;
   memset(&k2, 0, sizeof(k2));
   k2.g = g;
   k2.st = b->st;
   k2.n_streams = b->n;
-  k2.counts = d_counts;
-  k2.frames = frames;
+  k2.counts = w.d_counts;
+  k2.frames = prefix;
+  k2.done = done;
   k2.feat = b->d_feat;
   k2.feat_stride = b->max_new_frames;
   k2.max_new_frames = b->max_new_frames;
@@ -605,50 +630,118 @@ int speedyBatchWriteDevice(speedyBatch b, const int16_t* d_in, int64_t stride_fr
   k2.tap_tension = b->d_tap_tension;
   k2.tap_speed = b->d_tap_speed;
   k2.tap_energy = b->d_tap_energy;
-  CU_TRY(launch_k2(k2, st));
-  if (b->profiling) CU_TRY(cudaEventRecord(b->ev[2], st));
+  prof_mark(b, sa, 1, true);
+  CU_TRY(launch_k2(k2, sa));
+  prof_mark(b, sa, 1, false);
+  return 1;
+}
 
+// resynthesis (K4) of the prefix (done, prefix] on stream ss
+int launch_resynthesis(const WriteCall& w, long long done, long long prefix, cudaStream_t ss) {
+  speedyBatch b = w.b;
   K4Params k4;
   memset(&k4, 0, sizeof(k4));
-  k4.g = g;
+  k4.g = b->g;
   k4.st = b->st;
   k4.n_streams = b->n;
   k4.hist = b->d_hist[b->hist_cur];
   k4.hist_stride = b->hist_stride;
-  k4.in = d_in;
-  k4.in_stride_frames = stride_frames;
-  k4.counts = d_counts;
-  k4.frames = frames;
+  k4.in = w.d_in;
+  k4.in_stride_frames = w.stride_frames;
+  k4.counts = w.d_counts;
+  k4.frames = prefix;
+  k4.done = done;
   k4.speeds = b->d_speeds;
   k4.speeds_stride = b->speeds_stride;
   k4.flush = 0;
   k4.out = b->d_out;
   k4.out_capacity = b->out_capacity;
   k4.threads_per_stream = b->cfg.threads_per_stream;
-  CU_TRY(launch_k4(k4, st));
-  if (b->profiling) CU_TRY(cudaEventRecord(b->ev[3], st));
+  prof_mark(b, ss, 2, true);
+  CU_TRY(launch_k4(k4, ss));
+  prof_mark(b, ss, 2, false);
+  return 1;
+}
 
+// after the last prefix: carry the input tail, advance the totals
+int launch_write_tail(const WriteCall& w, cudaStream_t st) {
+  speedyBatch b = w.b;
   TailParams tp;
   memset(&tp, 0, sizeof(tp));
-  tp.g = g;
+  tp.g = b->g;
   tp.st = b->st;
   tp.n_streams = b->n;
   tp.hist_src = b->d_hist[b->hist_cur];
   tp.hist_dst = b->d_hist[b->hist_cur ^ 1];
   tp.hist_stride = b->hist_stride;
-  tp.in = d_in;
-  tp.in_stride_frames = stride_frames;
-  tp.counts = d_counts;
-  tp.frames = frames;
+  tp.in = w.d_in;
+  tp.in_stride_frames = w.stride_frames;
+  tp.counts = w.d_counts;
+  tp.frames = w.frames;
+  prof_mark(b, st, 3, true);
   CU_TRY(launch_tail(tp, st));
-  if (b->profiling) {
-    CU_TRY(cudaEventRecord(b->ev[4], st));
-    b->ev_recorded |= 1;
-  }
+  prof_mark(b, st, 3, false);
   b->hist_cur ^= 1;
-  b->last_frames = frames;
-  b->last_d_counts = d_counts;
+  b->last_frames = w.frames;
+  b->last_d_counts = w.d_counts;
   return 1;
+}
+
+int ensure_aux_streams(speedyBatch b) {
+  if (b->s_sonic) return 1;
+  CU_TRY(cudaStreamCreateWithFlags(&b->s_sonic, cudaStreamNonBlocking));
+  for (int i = 0; i < kPipeEvents; i++) CU_TRY(cudaEventCreateWithFlags(&b->ev_pipe[i], cudaEventDisableTiming));
+  return 1;
+}
+
+}  // namespace
+
+// A long write is cut into a few prefixes: the analysis kernels of prefix c+1 run on
+// the caller's stream while the resynthesis kernel of prefix c runs on an internal
+// one (they meet only through the speeds array), which hides the analysis behind the
+// latency-bound splice chain.  Everything is ordered after earlier work on the
+// caller's stream and the caller's stream waits for the internal one before the call
+// returns control to it, so the call still behaves like work on one stream.
+int speedyBatchWriteDevice(speedyBatch b, const int16_t* d_in, int64_t stride_frames, int64_t frames,
+                           const int32_t* d_counts, void* cuda_stream) {
+  if (!b) return 0;
+  if (frames < 0 || frames > b->cfg.max_write_frames) {
+    set_error("speedyBatchWriteDevice: frames exceeds max_write_frames");
+    return 0;
+  }
+  if (frames == 0) return 1;
+  CU_TRY(cudaSetDevice(b->cfg.device));
+  cudaStream_t st = pick_stream(b, cuda_stream);
+  WriteCall w = {b, d_in, stride_frames, frames, d_counts};
+  int parts = 1;
+  if (frames >= 8LL * b->g.rate) parts = 6;       // >= 8 s of audio per stream
+  else if (frames >= 2LL * b->g.rate) parts = 3;
+  if (const char* e = getenv("SPEEDY_B200_WRITE_PARTS")) parts = atoi(e) > 0 ? atoi(e) : parts;
+  if (parts > kPipeEvents - 2) parts = kPipeEvents - 2;
+  if (parts == 1) {
+    if (!launch_analysis(w, 0, frames, st) || !launch_resynthesis(w, 0, frames, st)) return 0;
+    return launch_write_tail(w, st);
+  }
+  if (!ensure_aux_streams(b)) return 0;
+  cudaStream_t ss = b->s_sonic;
+  // fork: the internal stream starts after everything already queued on the caller's
+  CU_TRY(cudaEventRecord(b->ev_pipe[kPipeEvents - 2], st));
+  CU_TRY(cudaStreamWaitEvent(ss, b->ev_pipe[kPipeEvents - 2], 0));
+  const long long step = b->g.step;
+  long long done = 0;
+  for (int c = 0; c < parts; c++) {
+    long long prefix = c == parts - 1 ? (long long)frames : ((long long)frames * (c + 1) / parts) / step * step;
+    if (prefix <= done) continue;
+    if (!launch_analysis(w, done, prefix, st)) return 0;
+    CU_TRY(cudaEventRecord(b->ev_pipe[c], st));
+    CU_TRY(cudaStreamWaitEvent(ss, b->ev_pipe[c], 0));
+    if (!launch_resynthesis(w, done, prefix, ss)) return 0;
+    done = prefix;
+  }
+  // join
+  CU_TRY(cudaEventRecord(b->ev_pipe[kPipeEvents - 1], ss));
+  CU_TRY(cudaStreamWaitEvent(st, b->ev_pipe[kPipeEvents - 1], 0));
+  return launch_write_tail(w, st);
 }
 
 int speedyBatchFlushDevice(speedyBatch b, void* cuda_stream) {
@@ -669,12 +762,9 @@ int speedyBatchFlushDevice(speedyBatch b, void* cuda_stream) {
   k4.out = b->d_out;
   k4.out_capacity = b->out_capacity;
   k4.threads_per_stream = b->cfg.threads_per_stream;
-  if (b->profiling) CU_TRY(cudaEventRecord(b->ev[4], st));
+  prof_mark(b, st, 4, true);
   CU_TRY(launch_k4(k4, st));
-  if (b->profiling) {
-    CU_TRY(cudaEventRecord(b->ev[5], st));
-    b->ev_recorded |= 2;
-  }
+  prof_mark(b, st, 4, false);
   return 1;
 }
 
@@ -782,38 +872,38 @@ int speedyBatchRead(speedyBatch b, int16_t* h_out, int64_t stride_frames, int32_
 int speedyBatchSetProfiling(speedyBatch b, int on) {
   if (!b) return 0;
   CU_TRY(cudaSetDevice(b->cfg.device));
-  if (on) {
-    for (int i = 0; i < 6; i++) {
-      if (!b->ev[i]) CU_TRY(cudaEventCreate(&b->ev[i]));
-    }
-  }
   b->profiling = on ? 1 : 0;
-  b->ev_recorded = 0;
+  b->prof_used = 0;
+  b->prof_marks.clear();
   return 1;
 }
 
-// Device time of the kernels of the last write (and flush): spectral, tension,
-// sonic, tail, flush-sonic, in milliseconds (CUDA events on the launching stream).
+// Device time of the kernels launched since profiling was switched on or this
+// function was last called: {spectral, tension, sonic, tail, flush-sonic}, each the
+// sum of its launches' durations in milliseconds (CUDA events on the launching
+// streams; launches on different streams may overlap in wall time).
 int speedyBatchGetKernelTimes(speedyBatch b, float* ms5) {
   if (!b || !ms5 || !b->profiling) return 0;
   CU_TRY(cudaSetDevice(b->cfg.device));
   for (int i = 0; i < 5; i++) ms5[i] = 0.0f;
-  if (b->ev_recorded & 1) {
-    CU_TRY(cudaEventSynchronize(b->ev[4]));
-    for (int i = 0; i < 4; i++) CU_TRY(cudaEventElapsedTime(&ms5[i], b->ev[i], b->ev[i + 1]));
+  CU_TRY(cudaDeviceSynchronize());
+  for (size_t i = 0; i + 1 < b->prof_marks.size(); i += 2) {
+    float ms = 0.0f;
+    if (cudaEventElapsedTime(&ms, b->prof_events[i], b->prof_events[i + 1]) == cudaSuccess) {
+      ms5[b->prof_marks[i].first] += ms;
+    }
   }
-  if (b->ev_recorded & 2) {
-    CU_TRY(cudaEventSynchronize(b->ev[5]));
-    CU_TRY(cudaEventElapsedTime(&ms5[4], b->ev[4], b->ev[5]));
-  }
+  b->prof_used = 0;
+  b->prof_marks.clear();
   return 1;
 }
 
-// One-shot over host buffers, pipelined in TIME: the input is cut into chunks of a
-// few seconds; while chunk c is being processed (the ordinary streaming write, state
-// carried on the device, bit-identical to one big write) chunk c+1 is on its way in
-// and the output chunk c-1 produced is on its way out.  The host->device copies,
-// the kernels and the device->host copies run on three CUDA streams.
+// One-shot over host buffers, pipelined in TIME.  The whole call is ONE logical
+// write whose data arrives progressively: the input crosses PCIe in chunks of a few
+// seconds into a full-size device staging buffer, and as soon as a chunk has landed
+// the kernels are launched over the prefix it completes (see kernels.cuh) - analysis
+// on one stream, resynthesis on another, the output each resynthesis launch added
+// going back to the host on a third while later chunks are still arriving.
 int speedyBatchProcess(speedyBatch b, const int16_t* h_in, int64_t frames, int16_t* h_out,
                        int64_t out_stride_frames, int32_t* h_out_counts) {
   if (!b || !h_in || !h_out || frames < 1) return 0;
@@ -829,38 +919,35 @@ int speedyBatchProcess(speedyBatch b, const int16_t* h_in, int64_t frames, int16
   chunk = (chunk + 7) & ~7LL;
   if (chunk > frames) chunk = frames;
   const int nchunks = (int)((frames + chunk - 1) / chunk);
-  if (!b->pipe_ready || b->pipe_chunk < chunk) {
-    for (int i = 0; i < 3; i++) {
-      if (!dev_alloc(b, &b->d_pipe[i], (size_t)n * chunk * C)) return 0;
-    }
-    if (!b->pipe_ready) {
-      int prio_lo = 0, prio_hi = 0;
-      cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);  // the copy-out kernel yields to compute
-      CU_TRY(cudaStreamCreateWithFlags(&b->s_h2d, cudaStreamNonBlocking));
-      CU_TRY(cudaStreamCreateWithPriority(&b->s_d2h, cudaStreamNonBlocking, prio_lo));
-    }
-    b->pipe_chunk = chunk;
+  if (!ensure_stage(b, frames) || !ensure_aux_streams(b)) return 0;
+  if (!b->pipe_ready) {
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);  // the copy-out kernel yields to compute
+    CU_TRY(cudaStreamCreateWithFlags(&b->s_h2d, cudaStreamNonBlocking));
+    CU_TRY(cudaStreamCreateWithPriority(&b->s_d2h, cudaStreamNonBlocking, prio_lo));
     b->pipe_ready = 1;
   }
-  cudaStream_t sc = b->own_stream;
-  if (!speedyBatchReset(b, sc)) return 0;
-  std::vector<cudaEvent_t> ev_in(nchunks), ev_done(nchunks), ev_out(nchunks);
+  cudaStream_t sa = b->own_stream;  // analysis
+  cudaStream_t ss = b->s_sonic;     // resynthesis
+  if (!speedyBatchReset(b, sa)) return 0;
+  std::vector<cudaEvent_t> ev_in(nchunks), ev_k2(nchunks), ev_done(nchunks), ev_out(nchunks);
   const bool trace = getenv("SPEEDY_B200_TRACE") != nullptr;  // developer aid: per-chunk timeline
   const unsigned ev_flags = trace ? cudaEventDefault : cudaEventDisableTiming;
   cudaEvent_t ev_t0 = nullptr;
   for (int c = 0; c < nchunks; c++) {
     CU_TRY(cudaEventCreateWithFlags(&ev_in[c], ev_flags));
+    CU_TRY(cudaEventCreateWithFlags(&ev_k2[c], ev_flags));
     CU_TRY(cudaEventCreateWithFlags(&ev_done[c], ev_flags));
     CU_TRY(cudaEventCreateWithFlags(&ev_out[c], ev_flags));
   }
-  if (trace) {
-    CU_TRY(cudaEventCreate(&ev_t0));
-    CU_TRY(cudaEventRecord(ev_t0, sc));
-    CU_TRY(cudaStreamWaitEvent(b->s_h2d, ev_t0, 0));
-  }
+  CU_TRY(cudaEventCreate(&ev_t0));
+  CU_TRY(cudaEventRecord(ev_t0, sa));  // after the reset
+  CU_TRY(cudaStreamWaitEvent(b->s_h2d, ev_t0, 0));
+  CU_TRY(cudaStreamWaitEvent(ss, ev_t0, 0));
   std::vector<long long> prev(n, 0);
   int ok = 1;
   const size_t in_pitch = (size_t)frames * C * sizeof(int16_t);
+  const size_t stage_pitch = (size_t)b->stage_frames * C * sizeof(int16_t);
   const size_t out_dpitch = (size_t)out_stride_frames * C * sizeof(int16_t);
   const size_t out_spitch = (size_t)b->out_capacity * C * sizeof(int16_t);
   // Is the caller's output buffer pinned, i.e. addressable from the device?  Then
@@ -874,7 +961,7 @@ int speedyBatchProcess(speedyBatch b, const int16_t* h_in, int64_t frames, int16
         attr.devicePointer != nullptr && !getenv("SPEEDY_B200_NO_ZEROCOPY")) {
       h_out_dev = static_cast<int16_t*>(attr.devicePointer);
     }
-    cudaGetLastError();  // a pageable pointer leaves a sticky-free error behind
+    cudaGetLastError();
   }
   if (h_out_dev && !b->d_done) {
     for (int i = 0; i < 3; i++) {
@@ -882,7 +969,7 @@ int speedyBatchProcess(speedyBatch b, const int16_t* h_in, int64_t frames, int16
     }
     if (!dev_alloc(b, &b->d_done, n)) return 0;
   }
-  if (h_out_dev) CU_TRY(cudaMemsetAsync(b->d_done, 0, sizeof(int) * n, sc));
+  if (h_out_dev) CU_TRY(cudaMemsetAsync(b->d_done, 0, sizeof(int) * n, ss));
   auto drain = [&](int c) -> int {
     if (h_out_dev) {
       // device-side scatter on the copy-out stream, ordered after chunk c's kernels
@@ -914,37 +1001,43 @@ int speedyBatchProcess(speedyBatch b, const int16_t* h_in, int64_t frames, int16
     }
     return 1;
   };
-  // chunk c travels in staging buffer c % 3; its copy is enqueued two chunks ahead
-  // of its kernels so the host->device stream never runs dry
-  auto enqueue_h2d = [&](int c) -> int {
+  // all host->device copies are queued up front: the copy stream never runs dry
+  for (int c = 0; c < nchunks; c++) {
     const long long f0 = (long long)c * chunk;
     const long long fc = frames - f0 < chunk ? frames - f0 : chunk;
-    const size_t row = (size_t)fc * C * sizeof(int16_t);
-    if (c >= 3) CU_TRY(cudaStreamWaitEvent(b->s_h2d, ev_done[c - 3], 0));
-    CU_TRY(cudaMemcpy2DAsync(b->d_pipe[c % 3], (size_t)chunk * C * sizeof(int16_t), h_in + f0 * C, in_pitch, row, n,
-                             cudaMemcpyHostToDevice, b->s_h2d));
+    CU_TRY(cudaMemcpy2DAsync(b->d_stage + f0 * C, stage_pitch, h_in + f0 * C, in_pitch,
+                             (size_t)fc * C * sizeof(int16_t), n, cudaMemcpyHostToDevice, b->s_h2d));
     CU_TRY(cudaEventRecord(ev_in[c], b->s_h2d));
-    return 1;
-  };
-  for (int c = 0; c < 2 && c < nchunks && ok; c++) ok = enqueue_h2d(c);
+  }
+  WriteCall w = {b, b->d_stage, b->stage_frames, frames, nullptr};
   for (int c = 0; c < nchunks && ok; c++) {
-    const long long f0 = (long long)c * chunk;
-    const long long fc = frames - f0 < chunk ? frames - f0 : chunk;
-    CU_TRY(cudaStreamWaitEvent(sc, ev_in[c], 0));
-    if (!speedyBatchWriteDevice(b, b->d_pipe[c % 3], chunk, fc, nullptr, sc)) ok = 0;
-    if (ok && c == nchunks - 1 && !speedyBatchFlushDevice(b, sc)) ok = 0;
+    const long long done = (long long)c * chunk;
+    const long long prefix = done + chunk < frames ? done + chunk : (long long)frames;
+    CU_TRY(cudaStreamWaitEvent(sa, ev_in[c], 0));
+    if (!launch_analysis(w, done, prefix, sa)) ok = 0;
+    CU_TRY(cudaEventRecord(ev_k2[c], sa));
+    CU_TRY(cudaStreamWaitEvent(ss, ev_k2[c], 0));
+    if (ok && !launch_resynthesis(w, done, prefix, ss)) ok = 0;
+    if (ok && c == nchunks - 1) {
+      // the flush needs the totals the tail advances: tail on sa after this K4, flush after it
+      CU_TRY(cudaEventRecord(ev_t0, ss));
+      CU_TRY(cudaStreamWaitEvent(sa, ev_t0, 0));
+      if (!launch_write_tail(w, sa)) ok = 0;
+      CU_TRY(cudaEventRecord(ev_t0, sa));
+      CU_TRY(cudaStreamWaitEvent(ss, ev_t0, 0));
+      if (ok && !speedyBatchFlushDevice(b, ss)) ok = 0;
+    }
     if (h_out_dev) {
       // the scatter of chunk c reads this snapshot while later chunks advance out_count;
       // snapshot c % 3 is free again once the scatter of chunk c - 3 has run
-      if (c >= 3) CU_TRY(cudaStreamWaitEvent(sc, ev_out[c - 3], 0));
-      CU_TRY(cudaMemcpyAsync(b->d_snap[c % 3], b->st.out_count, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, sc));
+      if (c >= 3) CU_TRY(cudaStreamWaitEvent(ss, ev_out[c - 3], 0));
+      CU_TRY(cudaMemcpyAsync(b->d_snap[c % 3], b->st.out_count, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, ss));
     }
     if (!h_out_dev || c == nchunks - 1) {
       CU_TRY(cudaMemcpyAsync(b->h_pinned_counts + (size_t)(c & 1) * n, b->st.out_count, sizeof(int32_t) * n,
-                             cudaMemcpyDeviceToHost, sc));
+                             cudaMemcpyDeviceToHost, ss));
     }
-    CU_TRY(cudaEventRecord(ev_done[c], sc));
-    if (ok && c + 2 < nchunks) ok = enqueue_h2d(c + 2);
+    CU_TRY(cudaEventRecord(ev_done[c], ss));
     if (h_out_dev) {
       if (ok) ok = drain(c);
       CU_TRY(cudaEventRecord(ev_out[c], b->s_d2h));
@@ -961,25 +1054,28 @@ int speedyBatchProcess(speedyBatch b, const int16_t* h_in, int64_t frames, int16
   if (h_out_counts) {
     for (int s = 0; s < n; s++) h_out_counts[s] = (int32_t)prev[s];
   }
-  read_finish_kernel<<<(n + 127) / 128, 128, 0, sc>>>(n, b->st.out_count, b->st.status, b->d_counts_stage,
+  if (cudaStreamSynchronize(b->s_d2h) != cudaSuccess) ok = 0;
+  read_finish_kernel<<<(n + 127) / 128, 128, 0, ss>>>(n, b->st.out_count, b->st.status, b->d_counts_stage,
                                                       out_stride_frames);
   count_launch();
-  if (cudaStreamSynchronize(b->s_d2h) != cudaSuccess) ok = 0;
   if (cudaStreamSynchronize(b->s_h2d) != cudaSuccess) ok = 0;
-  if (cudaStreamSynchronize(sc) != cudaSuccess) ok = 0;
+  if (cudaStreamSynchronize(ss) != cudaSuccess) ok = 0;
+  if (cudaStreamSynchronize(sa) != cudaSuccess) ok = 0;
   if (trace) {
     for (int c = 0; c < nchunks; c++) {
-      float a = 0, d = 0, o = 0;
-      cudaEventElapsedTime(&a, ev_t0, ev_in[c]);
-      cudaEventElapsedTime(&d, ev_t0, ev_done[c]);
-      if (h_out_dev) cudaEventElapsedTime(&o, ev_t0, ev_out[c]);
-      fprintf(stderr, "[speedyBatchProcess] chunk %2d: h2d done %7.2f ms, kernels done %7.2f ms, out done %7.2f ms\n", c,
-              a, d, o);
+      float a = 0, k = 0, d = 0, o = 0;
+      cudaEventElapsedTime(&a, ev_in[0], ev_in[c]);
+      cudaEventElapsedTime(&k, ev_in[0], ev_k2[c]);
+      cudaEventElapsedTime(&d, ev_in[0], ev_done[c]);
+      if (h_out_dev) cudaEventElapsedTime(&o, ev_in[0], ev_out[c]);
+      fprintf(stderr, "[speedyBatchProcess] chunk %2d (ms after the first h2d): h2d %7.2f analysis %7.2f "
+              "resynthesis %7.2f out %7.2f\n", c, a, k, d, o);
     }
-    cudaEventDestroy(ev_t0);
   }
+  cudaEventDestroy(ev_t0);
   for (int c = 0; c < nchunks; c++) {
     cudaEventDestroy(ev_in[c]);
+    cudaEventDestroy(ev_k2[c]);
     cudaEventDestroy(ev_done[c]);
     cudaEventDestroy(ev_out[c]);
   }

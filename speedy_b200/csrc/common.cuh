@@ -183,6 +183,20 @@ struct StreamState {
   long long* hist_base;
 };
 
+// Frames of a stream visible in a launch over the prefix (done, frames] of a write.
+struct Range {
+  long long t_old, t_done, t_new;
+};
+__device__ __forceinline__ Range write_range(const long long* total, const int32_t* counts, long long frames,
+                                             long long done, int s) {
+  Range r;
+  r.t_old = total[s];
+  const long long c = counts ? counts[s] : frames;
+  r.t_done = r.t_old + (c < done ? c : done);
+  r.t_new = r.t_old + (c < frames ? c : frames);
+  return r;
+}
+
 __host__ __device__ inline int frames_analyzed(const Geometry& g, long long total) {
   if (total < g.window + 1) return 0;
   return (int)((total - g.window - 1) / g.step) + 1;

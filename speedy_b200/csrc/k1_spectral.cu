@@ -172,11 +172,12 @@ __global__ void __launch_bounds__(WARPS * 32) k1_spectral_480(K1Params p) {
   if (s >= p.n_streams) return;
 
   const Geometry& g = p.g;
-  const long long t_old = p.st.total[s];
-  const long long t_new = t_old + (p.counts ? p.counts[s] : p.frames);
-  const int kA = frames_analyzed(g, t_old);
+  const Range rg = write_range(p.st.total, p.counts, p.frames, p.done, s);
+  const long long t_old = rg.t_old, t_new = rg.t_new;
+  const int kA = frames_analyzed(g, t_old);          // scratch rows count from here
+  const int kD = frames_analyzed(g, rg.t_done);      // first window of this launch
   const int kB = frames_analyzed(g, t_new);
-  const int k0 = kA + run * kRun;  // first new window of this run
+  const int k0 = kD + run * kRun;  // first new window of this run
   if (k0 >= kB) return;
   const int k1 = min(k0 + kRun, kB);
 
@@ -400,11 +401,12 @@ __global__ void __launch_bounds__(THREADS) k1_spectral_generic(K1Params p) {
   const int run = (int)(item % p.runs_per_stream);
   if (s >= p.n_streams) return;
 
-  const long long t_old = p.st.total[s];
-  const long long t_new = t_old + (p.counts ? p.counts[s] : p.frames);
-  const int kA = frames_analyzed(g, t_old);
+  const Range rg = write_range(p.st.total, p.counts, p.frames, p.done, s);
+  const long long t_old = rg.t_old, t_new = rg.t_new;
+  const int kA = frames_analyzed(g, t_old);          // scratch rows count from here
+  const int kD = frames_analyzed(g, rg.t_done);      // first window of this launch
   const int kB = frames_analyzed(g, t_new);
-  const int k0 = kA + run * kRun;
+  const int k0 = kD + run * kRun;
   if (k0 >= kB) return;
   const int k1 = min(k0 + kRun, kB);
 

@@ -43,13 +43,13 @@ __global__ void __launch_bounds__(kWarps * 32) k2_tension(K2Params p, float alph
   const float nonlinear = p.st.nonlinear[s];
   if (nonlinear == 0.0f) return;  // soniclib.c:397-399: Speedy is bypassed
 
-  const long long t_old = p.st.total[s];
-  const long long t_new = t_old + (p.counts ? p.counts[s] : p.frames);
-  const int kA = frames_analyzed(g, t_old);
-  const int kB = frames_analyzed(g, t_new);
+  const Range rg = write_range(p.st.total, p.counts, p.frames, p.done, s);
+  const int kA = frames_analyzed(g, rg.t_old);   // scratch rows count from here
+  const int kD = frames_analyzed(g, rg.t_done);  // first window of this launch
+  const int kB = frames_analyzed(g, rg.t_new);
   const int rA = tensions_ready(g, kA);
   const int F = g.future, B = g.past;
-  if (kB == kA) return;
+  if (kB == kD) return;
 
   float lp_e = p.st.lp_energy[s];
   float lp_d = p.st.lp_diff[s];
@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(kWarps * 32) k2_tension(K2Params p, float alph
   // bring in the carried ring: the last kRing at_times (slot = at_time & 31)
   {
     const size_t base = (size_t)s * kRing;
-    const int a_last = kA;  // newest at_time already stored (0 = none)
+    const int a_last = kD;  // newest at_time already stored (0 = none)
     // entry for at_time t lives at ring[t & 63]; only t in (a_last-32, a_last] exist
     const int t = a_last - lane;
     const bool ok = t >= 1;
@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(kWarps * 32) k2_tension(K2Params p, float alph
   const float2* feat = p.feat + (size_t)s * p.feat_stride;
   float* speeds = p.speeds + (size_t)s * p.speeds_stride;
 
-  for (int j0 = 0; j0 < kB - kA; j0 += 32) {
+  for (int j0 = kD - kA; j0 < kB - kA; j0 += 32) {
     const int j = j0 + lane;
     const bool have = j < kB - kA;
     const int a = kA + j + 1;  // at_time of window kA + j (soniclib.c:296)

@@ -638,8 +638,10 @@ __global__ void __launch_bounds__(NW * 32, MINB) k4_sonic(K4Params p) {
   }
   k.sync();
 
-  const long long t_old = p.st.total[s];
-  const long long t_new = p.flush ? t_old : t_old + (p.counts ? p.counts[s] : p.frames);
+  const Range rg = write_range(p.st.total, p.counts, p.frames, p.done, s);
+  const long long t_old = rg.t_old;
+  const long long t_new = p.flush ? t_old : rg.t_new;
+  const long long t_done = p.flush ? t_old : rg.t_done;
   k.src.channels = g.channels;
   k.src.hist = p.hist + (size_t)s * p.hist_stride;
   k.src.in = p.in ? p.in + (size_t)s * p.in_stride_frames * g.channels : nullptr;
@@ -672,12 +674,12 @@ __global__ void __launch_bounds__(NW * 32, MINB) k4_sonic(K4Params p) {
   int rA = 0;
   if (!p.flush) {
     if (nonlinear) {
-      rA = tensions_ready(g, frames_analyzed(g, t_old));
-      ev = rA;
+      rA = tensions_ready(g, frames_analyzed(g, t_old));  // the speeds rows count from here
+      ev = tensions_ready(g, frames_analyzed(g, t_done));
       ev_end = tensions_ready(g, frames_analyzed(g, t_new));
     } else {
       ev = 0;
-      ev_end = t_new > t_old ? 1 : 0;
+      ev_end = t_new > t_done ? 1 : 0;
     }
   } else if (nonlinear) {
     ev = k.fed / k.S;
@@ -700,9 +702,9 @@ __global__ void __launch_bounds__(NW * 32, MINB) k4_sonic(K4Params p) {
     } else if (nonlinear) {
       if (per_frame_speed) {
         const int j = (int)(ev - rA);
-        if ((j & 31) == 0) {
-          const long long idx = (long long)j + k.lane;
-          speed_batch = idx < ev_end - rA ? sp[idx] : 0.0f;
+        if ((j & 31) == 0 || i == 0) {
+          const long long idx = (long long)(j & ~31) + k.lane;
+          speed_batch = idx < ev_end - rA ? sp[idx] : 0.0f;  // rows past this launch are not ready
         }
         speed = __shfl_sync(kFull, speed_batch, j & 31);
       }

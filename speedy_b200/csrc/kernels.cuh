@@ -1,4 +1,11 @@
 // Kernel parameter blocks and host-side launchers (one .cu per kernel family).
+//
+// A write of L frames per stream may be processed as several launches over growing
+// prefixes (done, frames] of the same write: the analysis kernels of a later prefix
+// then overlap the resynthesis kernel of an earlier one (they only meet through the
+// speeds array), and in speedyBatchProcess a prefix can be processed while the rest
+// of the write is still crossing PCIe.  `done` = 0, `frames` = L is the one-launch case.
+// Scratch rows stay indexed from the first new frame of the whole write.
 #pragma once
 
 #include "common.cuh"
@@ -24,7 +31,8 @@ struct K1Params {
   const int16_t* in;             // caller's device buffer (may be null if frames == 0)
   long long in_stride_frames;
   const int32_t* counts;         // optional per-stream frame counts
-  long long frames;              // uniform frame count
+  long long frames;              // frames of this write visible so far (a prefix)
+  long long done;                // prefix already handled by earlier launches of this write
   // per-call scratch out: [n][feat_stride] (energy, raw spectral difference)
   float2* feat;
   int feat_stride;
@@ -48,7 +56,8 @@ struct K2Params {
   StreamState st;
   int n_streams;
   const int32_t* counts;
-  long long frames;
+  long long frames;              // visible prefix of this write
+  long long done;                // prefix already handled
   const float2* feat;            // from K1, [n][feat_stride]
   int feat_stride;
   int max_new_frames;
@@ -74,7 +83,8 @@ struct K4Params {
   const int16_t* in;
   long long in_stride_frames;
   const int32_t* counts;
-  long long frames;
+  long long frames;              // visible prefix of this write
+  long long done;                // prefix already handled
   const float* speeds;           // from K2
   int speeds_stride;
   int flush;                     // 1: this launch is sonicFlushStream
