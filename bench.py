@@ -49,6 +49,23 @@ METRIC = "batched real-time factor (audio-seconds processed per second)"
 UNIT = "audio-s/s"
 
 
+def ncu_traffic(kernel_substr):
+    """dram read + write bytes of one launch of the named kernel over the whole batch,
+    from the committed ncu --set full capture (profiles/r01_kernels.json, taken with
+    SPEEDY_B200_WRITE_PARTS=1 so that one launch covers the step)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_kernels.json")) as f:
+            ks = json.load(f)["kernels"]
+        best = None
+        for k in ks:
+            if kernel_substr in k["kernel"] and (best is None or k["duration"] > best["duration"]):
+                best = k
+        scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+        return int(best["dram_read"] * scale[best["dram_read_unit"]] + best["dram_write"] * scale[best["dram_write_unit"]])
+    except Exception:
+        return None
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -291,7 +308,9 @@ def run_cuda_arm(args):
         roofline = {
             "bound": "hbm", "kernel": "k4_sonic" if dominant == "sonic" else "k1_spectral_480",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": None, "peak_source": peak_src,
+            "traffic": ncu_traffic("k4_sonic" if dominant == "sonic" else "k1_spectral") if n == 1024 and SECONDS == 60 else None,
+            "traffic_source": "profiles/r01_kernels.json (ncu --set full, one launch per step)",
+            "peak_source": peak_src,
             "algorithmic_bytes_per_launch": alg[dominant], "kernel_ms": dom_ms,
             "kernel_ms_all": kt,
             "whole_path": {"algorithmic_bytes_per_step": in_bytes + out_bytes,
@@ -302,8 +321,8 @@ def run_cuda_arm(args):
         if world == 1 and not args.no_cpu_baseline:
             ol, kind = load_reference()
             cores = os.cpu_count() or 1
-            per_core = 4
-            ns = per_core * cores
+            per_core = 16  # ~45 CPU-seconds of work in total, a few seconds of wall time
+            ns = min(n, per_core * cores)
             pcm = h_in[:ns].numpy()
             if ns > n:
                 pcm = cpu_sample(ol, ns, SECONDS)

@@ -165,11 +165,15 @@ class Batch:
             raise RuntimeError("%s failed: %s" % (what, last_error()))
 
     def close(self):
-        if self.h:
-            lib().speedyBatchDestroy(self.h)
-            self.h = None
+        if getattr(self, "h", None) and _lib is not None:
+            _lib.speedyBatchDestroy(self.h)
+        self.h = None
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def reset(self, stream=None):
         self._ok(lib().speedyBatchReset(self.h, stream), "speedyBatchReset")

@@ -89,6 +89,18 @@ def test_resynthesis_bit_exact_given_oracle_speeds(golden_inputs, speed, feedbac
     assert np.array_equal(outs[0], o["out"])
 
 
+@pytest.mark.parametrize("tps", [64, 128])
+@pytest.mark.parametrize("rate,channels,speed", [(16000, 1, 2.0), (48000, 2, 1.5), (22050, 1, 0.6)])
+def test_multi_warp_resynthesis_variants(rate, channels, speed, tps):
+    """The 2- and 4-warp-per-stream variants of the Sonic kernel (threads_per_stream 64 /
+    128) produce the same bytes as the oracle."""
+    pcm = ol.synth(11, 2, rate, channels, rate * 2)
+    for s in range(2):
+        o = oracle_run(pcm[s], rate, speed)
+        outs, _, _ = gpu_process(pcm[s:s + 1], rate, speed, override=o["speed"][None], taps=0, tps=tps)
+        assert np.array_equal(outs[0], o["out"]), s
+
+
 def test_end_to_end_own_speeds_tapestry(golden_inputs):
     pcm, rate = golden_inputs["tapestry16k"]
     o = oracle_run(pcm, rate, 3.0)
