@@ -62,6 +62,15 @@ def build(force=False, verbose=False):
         if verbose:
             print(" ".join(cmd))
         subprocess.run(cmd, check=True)
+    # the speedy_wave-compatible command-line tool (host C++ only, links the library)
+    tool_src = os.path.join(HERE, "..", "tools", "speedy_wave.cpp")
+    tool = os.path.join(HERE, "speedy_wave")
+    if os.path.exists(tool_src) and (force or _stale(tool, [tool_src, OUT] + headers)):
+        cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-I" + os.path.join(HERE, "..", "include"), tool_src,
+               "-L" + HERE, "-lspeedy_b200", "-Wl,-rpath,$ORIGIN", "-o", tool]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.run(cmd, check=True)
     return OUT
 
 
