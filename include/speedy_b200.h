@@ -90,6 +90,12 @@ int sonicIntGetNumChannels(sonicStream stream);
 int sonicIntGetSampleRate(sonicStream stream);
 float sonicIntGetSpeed(sonicStream stream);
 int sonicIntSamplesAvailable(sonicStream stream);
+/* Plain Sonic on the same handle (sonic_test.cc:729-752).  Valid while the nonlinear
+ * factor is 0; otherwise the write and flush return 0. */
+void sonicIntSetSpeed(sonicStream stream, float speed);
+int sonicIntWriteShortToStream(sonicStream stream, const short* inBuffer, int sampleCount);
+int sonicIntReadShortFromStream(sonicStream stream, short* outBuffer, int bufferSize);
+int sonicIntFlushStream(sonicStream stream);
 
 /* ======================================================================== *
  * 2. Batched multi-stream API (new)

@@ -103,6 +103,10 @@ def lib():
         "sonicIntGetSampleRate": (C.c_int, [vp]),
         "sonicIntGetSpeed": (C.c_float, [vp]),
         "sonicIntSamplesAvailable": (C.c_int, [vp]),
+        "sonicIntSetSpeed": (None, [vp, C.c_float]),
+        "sonicIntWriteShortToStream": (C.c_int, [vp, i16p, C.c_int]),
+        "sonicIntReadShortFromStream": (C.c_int, [vp, i16p, C.c_int]),
+        "sonicIntFlushStream": (C.c_int, [vp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)

@@ -71,6 +71,16 @@ def build(force=False, verbose=False):
         if verbose:
             print(" ".join(cmd))
         subprocess.run(cmd, check=True)
+    # the evaluation tools (DTW / Teager / slopes), host C++ only
+    eval_src = os.path.join(HERE, "..", "tools", "eval_tools.cpp")
+    eval_lib = os.path.join(HERE, "libspeedy_eval.so")
+    eval_hdr = os.path.join(HERE, "..", "include", "speedy_eval.h")
+    if os.path.exists(eval_src) and (force or _stale(eval_lib, [eval_src, eval_hdr])):
+        cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-fPIC", "-shared", "-ffp-contract=off",
+               "-I" + os.path.join(HERE, "..", "include"), eval_src, "-o", eval_lib]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.run(cmd, check=True)
     return OUT
 
 

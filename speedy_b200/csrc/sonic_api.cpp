@@ -29,6 +29,8 @@ struct sonicStreamStruct {
   int window, fft, step;
   int buffer_size;  // 0 until the first nonlinear write (soniclib.c:195, 672-680)
   bool started;
+  int last_mode;     // -1 nothing written yet, 0 last write was linear, 1 nonlinear
+  bool flushed;      // nothing pending since the last sonicFlushStream
   long long out_capacity;
   std::vector<short> fifo;     // produced, not yet read (interleaved)
   std::vector<short> scratch;  // one batch read
@@ -120,9 +122,21 @@ static int write_frames(sonicStream s, const short* in, int count) {
   if (!s) return 0;
   if (s->rate != 1.0f) return 0;  // playback-rate conversion is not on this path
   if (!ensure_batch(s)) return 0;
-  if (!s->started) {
-    s->started = true;
+  s->started = true;
+  // A flushed handle that switches between the linear short circuit and Speedy starts
+  // Speedy's clock at zero, as the reference does (its Speedy stream only ever sees the
+  // nonlinear writes, soniclib.c:397-399; the flushed inner Sonic FIFO is empty).  Sonic's
+  // previous-period memory is the one thing not carried across.
+  const int mode = s->nonlinear != 0.0f ? 1 : 0;
+  if (s->last_mode >= 0 && s->last_mode != mode && s->flushed) {
+    if (!speedyBatchReset(s->batch, nullptr)) return 0;
+    s->spec_time = 0;
+    s->tension_time = 0;
+    for (auto& row : s->spec_ring) row.clear();
+    std::fill(s->normalized.begin(), s->normalized.end(), 0.0f);
   }
+  s->last_mode = mode;
+  s->flushed = false;
   if (s->nonlinear != 0.0f && s->buffer_size == 0) s->buffer_size = s->step;
   for (int done = 0; done < count;) {
     const int n = std::min(count - done, kChunkFrames);
@@ -148,6 +162,8 @@ sonicStream sonicCreateStream(int sampleRate, int numChannels) {
   s->batch = nullptr;
   s->buffer_size = 0;
   s->started = false;
+  s->last_mode = -1;
+  s->flushed = false;
   s->on_tension = nullptr;
   s->on_speed = nullptr;
   s->on_features = nullptr;
@@ -225,6 +241,7 @@ void sonicSetSpeed(sonicStream s, float speed) {
 int sonicFlushStream(sonicStream s) {
   if (!s || !ensure_batch(s)) return 0;
   if (!speedyBatchFlush(s->batch)) return 0;
+  s->flushed = true;
   return drain_device_output(s) ? 1 : 0;
 }
 
@@ -260,5 +277,22 @@ int sonicIntGetNumChannels(sonicStream s) { return s ? s->channels : 0; }
 int sonicIntGetSampleRate(sonicStream s) { return s ? s->sample_rate : 0; }
 float sonicIntGetSpeed(sonicStream s) { return s ? s->speed : 0.0f; }
 int sonicIntSamplesAvailable(sonicStream s) { return s ? (int)(s->fifo.size() / s->channels) : 0; }
+
+// The inner Sonic stream under its SONIC_INTERNAL names (sonic2.h:22-35), as
+// sonic_test.cc:729-752 drives it: plain Sonic at the handle's speed.  Only valid while
+// Speedy is switched off; with a nonlinear factor set these refuse (return 0) rather
+// than bypass the analysis.
+void sonicIntSetSpeed(sonicStream s, float speed) { sonicSetSpeed(s, speed); }
+int sonicIntWriteShortToStream(sonicStream s, const short* inBuffer, int sampleCount) {
+  if (!s || s->nonlinear != 0.0f) return 0;
+  return sonicWriteShortToStream(s, inBuffer, sampleCount);
+}
+int sonicIntReadShortFromStream(sonicStream s, short* outBuffer, int bufferSize) {
+  return sonicReadShortFromStream(s, outBuffer, bufferSize);
+}
+int sonicIntFlushStream(sonicStream s) {
+  if (!s || s->nonlinear != 0.0f) return 0;
+  return sonicFlushStream(s);
+}
 
 }  // extern "C"
