@@ -131,3 +131,26 @@ def test_chunked_writes_equal_one_write():
     got.append(buf[:n].copy())
     lib.sonicIntDestroyStream(s)
     assert np.array_equal(np.concatenate(got), whole[:, 0])
+
+
+def test_speech_sample_dtw_with_reference_thresholds(golden_inputs):
+    """sonic_test.cc:641-724 on the CPU restatement: the DTW path between the original
+    and the time-compressed spectrograms has slope 1/speed within the reference's own
+    tolerances — a statistical pin of the restated Sonic (its upstream source is absent)."""
+    from speedy_b200 import evaluation as ev
+    from test_sonic_suite import compute_spectrogram
+    pcm, rate = golden_inputs["tapestry16k"]
+    speed = 3.0
+    linear = ol.port_process(ol.cfg(rate, speed=speed, nonlinear=0.0), pcm, taps=False)["out"][:, 0]
+    speedy = ol.port_process(ol.cfg(rate, speed=speed, nonlinear=1.0), pcm, taps=False)["out"][:, 0]
+    assert abs(len(linear) - 50381 / speed) <= 140
+    original_spec = compute_spectrogram(pcm[:, 0], rate)
+    for result, tol, max_cost in ((linear, 0.02, 13000000), (speedy, 0.1, None)):
+        cost, p1, p2 = ev.dtw(original_spec, compute_spectrogram(result, rate))
+        if max_cost:
+            assert cost < max_cost
+        slope = ev.linear_slope(p1, p2)
+        assert abs(slope - 1.0 / speed) <= tol
+        slopes = ev.linear_slope_everywhere(p1, p2, 10)
+        assert abs(ev.mean(slopes) - slope) <= 0.02
+        assert ev.standard_deviation(slopes) < 0.2
