@@ -8,8 +8,9 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OUT = os.path.join(HERE, "libspeedy_b200.so")
-BUILD = os.path.join(HERE, "_build")
+# developer builds (A/B variants, -DK4_TIMING) can go elsewhere; see SPEEDY_B200_LIB in __init__.py
+OUT = os.environ.get("SPEEDY_B200_BUILD_OUT") or os.path.join(HERE, "libspeedy_b200.so")
+BUILD = os.environ.get("SPEEDY_B200_BUILD_DIR") or os.path.join(HERE, "_build")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC,-O2,-Wall", "-I" + CSRC]
@@ -65,7 +66,7 @@ def build(force=False, verbose=False):
     # the speedy_wave-compatible command-line tool (host C++ only, links the library)
     tool_src = os.path.join(HERE, "..", "tools", "speedy_wave.cpp")
     tool = os.path.join(HERE, "speedy_wave")
-    if os.path.exists(tool_src) and (force or _stale(tool, [tool_src, OUT] + headers)):
+    if os.path.exists(tool_src) and not os.environ.get("SPEEDY_B200_BUILD_OUT") and (force or _stale(tool, [tool_src, OUT] + headers)):
         cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-I" + os.path.join(HERE, "..", "include"), tool_src,
                "-L" + HERE, "-lspeedy_b200", "-Wl,-rpath,$ORIGIN", "-o", tool]
         if verbose:

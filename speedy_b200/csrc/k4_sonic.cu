@@ -46,10 +46,13 @@
 
 namespace speedy {
 
+#ifdef K4_TIMING
+__device__ unsigned long long g_k4_cycles[16];
+#endif
+
 namespace {
 
 #ifdef K4_TIMING
-__device__ unsigned long long g_k4_cycles[16];
 #define T_BEGIN() const long long _t0 = clock64()
 #define T_END(slot) do { if (vl == 0 && timing) atomicAdd(&g_k4_cycles[slot], (unsigned long long)(clock64() - _t0)); } while (0)
 #else
@@ -783,3 +786,14 @@ cudaError_t launch_k4(const K4Params& p0, cudaStream_t stream) {
 }
 
 }  // namespace speedy
+
+#ifdef K4_TIMING
+// developer build only (SPEEDY_K4_TIMING=1): read / reset the per-phase cycle counters
+extern "C" void speedyDebugK4Cycles(unsigned long long* out, int reset) {
+  if (out) cudaMemcpyFromSymbol(out, speedy::g_k4_cycles, sizeof(unsigned long long) * 16);
+  if (reset) {
+    unsigned long long z[16] = {0};
+    cudaMemcpyToSymbol(speedy::g_k4_cycles, z, sizeof(z));
+  }
+}
+#endif
