@@ -64,15 +64,15 @@ constexpr int kPad = 32;  // over-read slack behind the window and the decimated
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kMaxGroups = 64;  // lag groups of four per search (>= 2 * skip + 2)
 
-template <int NW>
+template <int NW, int CH>
 struct Sonic {
   static constexpr int VL = 32 * NW;  // lanes cooperating on one stream
   // geometry
-  int C, S, minP, maxP, maxReq, skip;
+  int Crt, S, minP, maxP, maxReq, skip;
   long long cap;
   // shared memory (this warp's slice)
   int* w32;                 // mono window, 32-bit [bufN + kPad]
-  short* buf;               // interleaved raw window (C > 1 only) [bufN * C]
+  short* buf;               // interleaved raw window ((CH ? CH : Crt) > 1 only) [bufN * (CH ? CH : Crt)]
   int* ds32;                // decimated mono [maxReq / skip + kPad]
   int bufN;
   // window state (warp-uniform)
@@ -106,7 +106,7 @@ struct Sonic {
     sync();  // every lane is done with the old window
     bufStart = start & ~7LL;  // keeps the 16-byte loads of the refill aligned
     bufLen = bufN;
-    stage_mono<VL, int>(src, bufStart, bufN, zero_from, w32, C > 1 ? buf : nullptr, vl);
+    stage_mono<VL, int>(src, bufStart, bufN, zero_from, w32, (CH ? CH : Crt) > 1 ? buf : nullptr, vl);
     sync();
     T_END(0);
   }
@@ -124,17 +124,17 @@ struct Sonic {
   // Append n frames starting at absolute frame `from` to the output.
   __device__ __forceinline__ void emit_copy(long long from, int n, int out_offset_frames) {
     const int o0 = (int)(from - bufStart);
-    const int total = n * C;
-    const long long base = (long long)(outCount + out_offset_frames) * C;
-    const long long room = cap * C - base;
+    const int total = n * (CH ? CH : Crt);
+    const long long base = (long long)(outCount + out_offset_frames) * (CH ? CH : Crt);
+    const long long room = cap * (CH ? CH : Crt) - base;
     short* o = out + base;
     T_BEGIN();
-    if (C == 1) {
+    if ((CH ? CH : Crt) == 1) {
       for (int i = vl; i < total; i += VL) {
         if (i < room) o[i] = (short)w32[o0 + i];
       }
     } else {
-      const short* p = buf + (size_t)o0 * C;
+      const short* p = buf + (size_t)o0 * (CH ? CH : Crt);
       for (int i = vl; i < total; i += VL) {
         if (i < room) o[i] = p[i];
       }
@@ -155,52 +155,86 @@ struct Sonic {
     return num < 0 ? -q : q;
   }
 
-  // out[t] = (down[t]*(n-t) + up[t]*t) / n per channel, C integer arithmetic.
+  // out[t] = (down[t]*(n-t) + up[t]*t) / n per channel, (CH ? CH : Crt) integer arithmetic.
   // down/up are absolute frames inside the window.
   __device__ __forceinline__ void overlap_add(int n, long long down, long long up, int out_offset_frames) {
     const int d0 = (int)(down - bufStart), u0 = (int)(up - bufStart);
-    const int total = n * C;
-    const long long base = (long long)(outCount + out_offset_frames) * C;
-    const long long room = cap * C - base;
+    const int total = n * (CH ? CH : Crt);
+    const long long base = (long long)(outCount + out_offset_frames) * (CH ? CH : Crt);
+    const long long room = cap * (CH ? CH : Crt) - base;
     short* o = out + base;
     T_BEGIN();
-    const float rcp_n = __frcp_rn((float)(n > 0 ? n : 1));
-    if (C == 1) {
-      for (int t = vl; t < total; t += VL) {
-        int v = div_trunc(w32[d0 + t] * (n - t) + w32[u0 + t] * t, n, rcp_n);
-        if (t < room) o[t] = (short)v;
+    // trunc(|num| / n) == umulhi(|num|, magic) >> shift for |num| < 2^25, 1 < n < 2^11,
+    // 2^shift < n <= 2^(shift+1), magic = ceil(2^(32+shift) / n)
+    unsigned magic = 0u;
+    int shift = 0;
+    if (n > 1) {
+      shift = 31 - __clz(n - 1);
+      const double qd = __ddiv_rn((double)(1ULL << (32 + shift)), (double)n);
+      magic = (unsigned)(unsigned long long)qd + ((n & (n - 1)) ? 1u : 0u);
+    }
+    if ((CH ? CH : Crt) == 1) {
+      if (n == 1) {
+        if (vl == 0 && 0 < room) o[0] = (short)w32[d0];
+      } else {
+        for (int t = vl; t < total; t += VL) {
+          const int num = w32[d0 + t] * (n - t) + w32[u0 + t] * t;
+          const int q = (int)(__umulhi((unsigned)abs(num), magic) >> shift);
+          if (t < room) o[t] = (short)(num < 0 ? -q : q);
+        }
       }
     } else {
-      const short* dp = buf + (size_t)d0 * C;
-      const short* up_ = buf + (size_t)u0 * C;
+      const short* dp = buf + (size_t)d0 * (CH ? CH : Crt);
+      const short* up_ = buf + (size_t)u0 * (CH ? CH : Crt);
       for (int i = vl; i < total; i += VL) {
-        int t = i / C;
-        int v = div_trunc((int)dp[i] * (n - t) + (int)up_[i] * t, n, rcp_n);
-        if (i < room) o[i] = (short)v;
+        int t = i / (CH ? CH : Crt);
+        const int num = (int)dp[i] * (n - t) + (int)up_[i] * t;
+        const int q = n == 1 ? abs(num) : (int)(__umulhi((unsigned)abs(num), magic) >> shift);
+        if (i < room) o[i] = (short)(num < 0 ? -q : q);
       }
     }
     T_END(6);
   }
 
-  // Upstream downSampleInput: sum `skip` frames x C channels, C integer division
+  // Upstream downSampleInput: sum `skip` frames x (CH ? CH : Crt) channels, (CH ? CH : Crt) integer division
   // (truncating).  |sum| < 2^21 and the divisor is small, so the quotient is exact
   // as (|sum| * ceil(2^32 / divisor)) >> 32.
   __device__ __forceinline__ void decimate(int off) {
     T_BEGIN();
     const int count = maxReq / skip;
-    const int per = C * skip;
-    {
+    const int per = (CH ? CH : Crt) * skip;
+    if ((CH ? CH : Crt) == 1 && (skip & 3) == 0) {
+      const int r = off & 3;
+      const int nmid = (skip >> 2) - 1;
+      const int* base = w32 + (off & ~3);
+#pragma unroll 2
+      for (int i = vl; i < count; i += VL) {
+        const int4* p = reinterpret_cast<const int4*>(base + i * skip);
+        const int4 x = p[0];
+        const int4 z = p[nmid + 1];
+        int v = x.w + (r == 0 ? x.x : z.x) + (r <= 1 ? x.y : z.y) + (r <= 2 ? x.z : z.z);
+#pragma unroll 1
+        for (int m = 1; m <= nmid; m++) {
+          const int4 t = p[m];
+          v += (t.x + t.y) + (t.z + t.w);
+        }
+        const int qa = (int)__umulhi((unsigned)abs(v), dec_magic);
+        ds32[i] = v < 0 ? -qa : qa;
+      }
+    } else {
+#pragma unroll 1
       for (int i = vl; i < count; i += VL) {
         int v = 0;
-        if (C == 1) {
+        if ((CH ? CH : Crt) == 1) {
           const int* q = w32 + off + i * skip;
-          int j = 0;
-          for (; j + 4 <= skip; j += 4) v += (q[j] + q[j + 1]) + (q[j + 2] + q[j + 3]);
-          for (; j < skip; j++) v += q[j];
+#pragma unroll 1
+          for (int j = 0; j < skip; j++) v += q[j];
         } else {
-          const short* q = buf + ((size_t)off + (size_t)i * skip) * C;
+          const short* q = buf + ((size_t)off + (size_t)i * skip) * (CH ? CH : Crt);
           int j = 0;
+#pragma unroll 1
           for (; j + 4 <= per; j += 4) v += (q[j] + q[j + 1]) + (q[j + 2] + q[j + 3]);
+#pragma unroll 1
           for (; j < per; j++) v += q[j];
         }
         const int qa = (int)__umulhi((unsigned)abs(v), dec_magic);
@@ -247,7 +281,7 @@ struct Sonic {
   }
 
   // Exact arg-min and arg-max of diff/period over the warp's candidates (one
-  // (diff, period) pair per lane for each, period 0 = none).  The C scan compares by
+  // (diff, period) pair per lane for each, period 0 = none).  The (CH ? CH : Crt) scan compares by
   // cross-multiplication with strict inequalities, so ties go to the smaller lag.
   // A float quotient picks the lanes within 2e-6 of the extremum (a superset of the
   // true extremum: its relative error is below 4e-7); almost always that is one
@@ -300,7 +334,7 @@ struct Sonic {
   }
 
   // Fold the four lag sums a lane holds (lags pg .. pg+3) into its running best /
-  // worst candidates; lags ascend, so strict comparisons reproduce the C scan.
+  // worst candidates; lags ascend, so strict comparisons reproduce the (CH ? CH : Crt) scan.
   __device__ __forceinline__ void fold(const unsigned (&d)[4], int pg, int lo, int hi, unsigned& bd, int& bp,
                                        unsigned& wd, int& wp) {
 #pragma unroll
@@ -417,7 +451,7 @@ struct Sonic {
     unsigned best_diff, worst_diff;
     int best, worst;
     pick2(bd, bp, wd, wp, &best_diff, &best, &worst_diff, &worst);
-    // the C scan starts from (maxDiff = 0, worstPeriod = 255) and only replaces
+    // the (CH ? CH : Crt) scan starts from (maxDiff = 0, worstPeriod = 255) and only replaces
     // it with a strictly larger ratio
     if (worst_diff == 0u) worst = 255;
     *minDiff = udiv_small(best_diff, best);
@@ -434,7 +468,7 @@ struct Sonic {
     const int* arr = w32;
     int aoff = off;
     int lo = minP, hi = maxP, stages = 1;
-    if (!(C == 1 && skip == 1)) {
+    if (!((CH ? CH : Crt) == 1 && skip == 1)) {
       decimate(off);
       arr = ds32;
       aoff = 0;
@@ -546,14 +580,14 @@ __host__ __device__ inline size_t k4_stream_smem(const Geometry& g, int buf_fram
 // MINB: resident CTAs per SM the register allocation is held to (1 = unconstrained).
 // Few streams: registers are free, latency is what counts.  Many streams: 16 resident
 // warps per SM hide the chain's latency, worth a tighter allocation.
-template <int NW, int MINB>
+template <int NW, int MINB, int CH>
 __global__ void __launch_bounds__(NW * 32, MINB) k4_sonic(K4Params p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int s = blockIdx.x;
   if (s >= p.n_streams) return;
   const Geometry& g = p.g;
 
-  Sonic<NW> k;
+  Sonic<NW, CH> k;
   k.lane = threadIdx.x & 31;
   k.warp = threadIdx.x >> 5;
   k.vl = threadIdx.x;
@@ -564,7 +598,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k4_sonic(K4Params p) {
 #else
   k.timing = false;
 #endif
-  k.C = g.channels;
+  k.Crt = g.channels;
   k.S = g.step;
   k.minP = g.min_period;
   k.maxP = g.max_period;
@@ -579,7 +613,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k4_sonic(K4Params p) {
   k.buf = reinterpret_cast<short*>(k.sums + 2 * 4 * kMaxGroups);
   k.bufStart = 0;
   k.bufLen = 0;
-  k.dec_magic = (unsigned)((0x100000000ULL + (unsigned)(k.C * k.skip) - 1) / (unsigned)(k.C * k.skip));
+  k.dec_magic = (unsigned)((0x100000000ULL + (unsigned)(g.channels * k.skip) - 1) / (unsigned)(g.channels * k.skip));
   {
     // lane mappings (lags rounded out to groups of four)
     const int c_lo = k.minP / k.skip, c_hi = k.maxP / k.skip;
@@ -635,7 +669,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k4_sonic(K4Params p) {
     k.fg = k.lane - slot * k.fG;
     k.fGi0 = slot < gpw ? k.warp * gpw + slot : (1 << 30);  // idle lanes never match
   }
-  for (int i = k.vl; i < kPad; i += Sonic<NW>::VL) {  // the over-read pads
+  for (int i = k.vl; i < kPad; i += Sonic<NW, CH>::VL) {  // the over-read pads
     k.w32[k.bufN + i] = 0;
     k.ds32[k.maxReq / k.skip + i] = 0;
   }
@@ -645,7 +679,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k4_sonic(K4Params p) {
   const long long t_old = rg.t_old;
   const long long t_new = p.flush ? t_old : rg.t_new;
   const long long t_done = p.flush ? t_old : rg.t_done;
-  k.src.channels = g.channels;
+  k.src.channels = CH ? CH : g.channels;
   k.src.hist = p.hist + (size_t)s * p.hist_stride;
   k.src.in = p.in ? p.in + (size_t)s * p.in_stride_frames * g.channels : nullptr;
   k.src.hist_base = p.st.hist_base[s];
@@ -756,18 +790,24 @@ static int k4_buf_frames(const Geometry& g, int n_streams) {
   return (n + 63) & ~63;
 }
 
-template <int NW, int MINB>
-static cudaError_t launch_k4_t(K4Params& p, cudaStream_t stream) {
+template <int NW, int MINB, int CH>
+static cudaError_t launch_k4_c(K4Params& p, cudaStream_t stream) {
   const size_t smem = k4_stream_smem(p.g, p.buf_frames);
   static size_t attr = 0;
   if (smem > attr) {
-    cudaError_t e = cudaFuncSetAttribute(k4_sonic<NW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e =
+        cudaFuncSetAttribute(k4_sonic<NW, MINB, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     attr = smem;
   }
-  k4_sonic<NW, MINB><<<p.n_streams, NW * 32, smem, stream>>>(p);
+  k4_sonic<NW, MINB, CH><<<p.n_streams, NW * 32, smem, stream>>>(p);
   count_launch();
   return cudaGetLastError();
+}
+
+template <int NW, int MINB>
+static cudaError_t launch_k4_t(K4Params& p, cudaStream_t stream) {
+  return p.g.channels == 1 ? launch_k4_c<NW, MINB, 1>(p, stream) : launch_k4_c<NW, MINB, 0>(p, stream);
 }
 
 cudaError_t launch_k4(const K4Params& p0, cudaStream_t stream) {
@@ -777,12 +817,13 @@ cudaError_t launch_k4(const K4Params& p0, cudaStream_t stream) {
   // bound and extra warps shorten it; with many streams one warp each is the most
   // work-efficient shape
   int t = p.threads_per_stream;
+  if (const char* e = getenv("SPEEDY_K4_THREADS")) t = atoi(e);
   if (t == 0) t = 32;  // measured: extra warps do not shorten the chain enough to pay for their barriers
   if (t <= 32) {
     return p.n_streams > 148 * 12 ? launch_k4_t<1, 16>(p, stream) : launch_k4_t<1, 1>(p, stream);
   }
-  if (t <= 64) return launch_k4_t<2, 1>(p, stream);
-  return launch_k4_t<4, 1>(p, stream);
+  if (t <= 64) return launch_k4_t<2, 7>(p, stream);
+  return launch_k4_t<4, 7>(p, stream);
 }
 
 }  // namespace speedy
