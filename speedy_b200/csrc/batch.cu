@@ -689,7 +689,11 @@ int launch_write_tail(const WriteCall& w, cudaStream_t st) {
 
 int ensure_aux_streams(speedyBatch b) {
   if (b->s_sonic) return 1;
-  CU_TRY(cudaStreamCreateWithFlags(&b->s_sonic, cudaStreamNonBlocking));
+  // the resynthesis chain is latency bound: its CTAs go first whenever an SM has room
+  int prio_lo = 0, prio_hi = 0;
+  CU_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  if (getenv("SPEEDY_B200_NO_PRIO")) prio_hi = prio_lo;
+  CU_TRY(cudaStreamCreateWithPriority(&b->s_sonic, cudaStreamNonBlocking, prio_hi));
   for (int i = 0; i < kPipeEvents; i++) CU_TRY(cudaEventCreateWithFlags(&b->ev_pipe[i], cudaEventDisableTiming));
   return 1;
 }

@@ -26,6 +26,8 @@
 //
 // Any other rate (N = 660, 720, 1440, ...) goes through the generic kernel: one
 // CTA per run, a mixed-radix Stockham FFT in shared memory.
+#include <stdlib.h>
+
 #include "kernels.cuh"
 
 namespace speedy {
@@ -380,6 +382,298 @@ __global__ void __launch_bounds__(WARPS * 32) k1_spectral_480(K1Params p) {
 }
 
 // ---------------------------------------------------------------------------
+// Mixed-radix path: any even window W whose half M = W/2 factors into radices
+// <= 16 (22.05 kHz: M = 165 = 5*3*11, 24 kHz: 180, 32 kHz: 240, 48 kHz: 360 ...).
+// One CTA per run of windows, two windows in flight.  The same decomposition as
+// the 16 kHz kernel: the zero-padded real N = 2W transform is the real-FFT split
+// of the W-point complex transform of z[m] = v[2m] + i v[2m+1] (m < M, zero
+// beyond), whose even / odd output bins are the M-point transforms of z[m] and
+// of z[m] W_W^m.  The four M-point transforms of a window pair run together as
+// an autosort (Stockham) FFT in shared memory, one thread per radix-R butterfly.
+// ---------------------------------------------------------------------------
+namespace {
+
+template <int R>
+__device__ __forceinline__ void small_dft(float2 (&a)[R], const float2* twM, int M) {
+  if (R == 2) {
+    const float2 t = a[1];
+    a[1] = csub(a[0], t);
+    a[0] = cadd(a[0], t);
+  } else if (R == 3) {
+    dft3(a[0], a[1], a[2]);
+  } else if (R == 4) {
+    dft4(a[0], a[1], a[2], a[3]);
+  } else if (R == 5) {
+    dft5(a[0], a[1], a[2], a[3], a[4]);
+  }
+}
+
+// One radix-R butterfly of the stage (n = R m, stride st): inputs x[q + st (pp + r m)],
+// outputs y[q + st (R pp + t)] = W_n^{pp t} sum_r x_r W_R^{r t};  W_n^{pp t} = W_M^{st pp t}.
+template <int R>
+__device__ __forceinline__ void butterfly(const float2* x, float2* y, const float2* twM, int M, int m, int st,
+                                          int pp, int q) {
+  float2 a[R];
+#pragma unroll
+  for (int r = 0; r < R; r++) a[r] = x[q + st * (pp + r * m)];
+  if constexpr (R == 8) dft8(a);
+  else small_dft<R>(a, twM, M);
+  const int tstep = st * pp;
+  y[q + st * (R * pp)] = a[0];
+#pragma unroll
+  for (int t = 1; t < R; t++) y[q + st * (R * pp + t)] = cmul(a[t], twM[tstep * t]);
+}
+
+// Any other (odd prime) radix up to 16: direct O(R^2) butterfly.
+__device__ __forceinline__ void butterfly_any(int R, const float2* x, float2* y, const float2* twM, int M, int m,
+                                              int st, int pp, int q) {
+  float2 a[16];
+  for (int r = 0; r < R; r++) a[r] = x[q + st * (pp + r * m)];
+  const int wr = M / R;
+  const int tstep = st * pp;
+  for (int t = 0; t < R; t++) {
+    float2 acc = a[0];
+    int e = 0;
+    for (int r = 1; r < R; r++) {
+      e += t;
+      if (e >= R) e -= R;
+      acc = cadd(acc, cmul(a[r], twM[wr * e]));
+    }
+    y[q + st * (R * pp + t)] = cmul(acc, twM[tstep * t]);
+  }
+}
+
+}  // namespace
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k1_spectral_mixed(K1Params p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const Geometry& g = p.g;
+  const int W = g.window, S = g.step, P = g.partial, N = g.fft, M = W / 2, HW = W / 2;
+  constexpr int NWARP = THREADS / 32;
+  float2* X = reinterpret_cast<float2*>(smem_raw);     // [4][M]
+  float2* Y = X + 4 * M;                                // [4][M]
+  float2* s_twM = Y + 4 * M;                            // [M]   W_M^k
+  float2* s_twW = s_twM + M;                            // [M]   W_W^m
+  float2* s_twN = s_twW + M;                            // [HW]  W_N^t
+  float* s_win = reinterpret_cast<float*>(s_twN + HW);  // [W]   Hamming / 32768
+  float* lmag = s_win + W;                              // [3][W]
+  float* red = lmag + 3 * W;                            // [NWARP][4]
+  short* samp = reinterpret_cast<short*>(red + NWARP * 4);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < M; i += THREADS) {
+    s_twM[i] = p.tw_n[4 * i];
+    s_twW[i] = p.tw_half[i];
+  }
+  for (int i = tid; i < HW; i += THREADS) s_twN[i] = p.tw_n[i];
+  for (int i = tid; i < W; i += THREADS) s_win[i] = p.window[i] * 3.0517578125e-05f;
+
+  const long long item = blockIdx.x;
+  const int s = (int)(item / p.runs_per_stream);
+  const int run = (int)(item % p.runs_per_stream);
+  if (s >= p.n_streams) return;
+  const Range rg = write_range(p.st.total, p.counts, p.frames, p.done, s);
+  const long long t_old = rg.t_old, t_new = rg.t_new;
+  const int kA = frames_analyzed(g, t_old);      // scratch rows count from here
+  const int kD = frames_analyzed(g, rg.t_done);  // first window of this launch
+  const int kB = frames_analyzed(g, t_new);
+  const int k0 = kD + run * kRun;
+  if (k0 >= kB) return;
+  const int k1 = min(k0 + kRun, kB);
+
+  Source src;
+  src.channels = g.channels;
+  src.hist = p.hist + (size_t)s * p.hist_stride;
+  src.in = p.in ? p.in + (size_t)s * p.in_stride_frames * g.channels : nullptr;
+  src.hist_base = p.st.hist_base[s];
+  src.t_old = t_old;
+  src.t_new = t_new;
+
+  // Stage the run's samples (mono down-mix) once: windows k0-1 .. k1-1.
+  const long long base = (long long)(k0 - 1) * S;
+  const int need = (k1 - k0 + 1) * S + P;
+  stage_mono<THREADS, short>(src, base, need, t_new, samp, nullptr, tid);
+  __syncthreads();
+
+  int ip = 0, ia = 1, ib = 2;  // rotating rows of lmag: previous window, slot A, slot B
+  float linv_prev = 0.0f;
+
+  for (int kk = k0 - 1; kk < k1; kk += 2) {
+    // ---- pass 0: int16 -> float, pre-emphasis, Hamming, packing ------------
+    for (int i = tid; i < 2 * M; i += THREADS) {
+      const int slot = i >= M ? 1 : 0;
+      const int m = i - slot * M;
+      const int k = kk + slot;
+      float2 z = make_float2(0.0f, 0.0f);
+      if (k >= 0 && k < k1) {
+        const int o = (k - (k0 - 1)) * S;
+        const int n = 2 * m;
+        // state entering sample 0 is the last sample of the previous window, i.e.
+        // sample P-1 of this one (speedy.c:416-425); 0 before the first window
+        const float xm = (float)((n > 0) ? samp[o + n - 1] : (k >= 1 ? samp[o + P - 1] : 0));
+        const float x0 = (float)samp[o + n];
+        const float x1 = (float)samp[o + n + 1];
+        const float y0 = __fmaf_rn(-kPreLo, xm, __fmaf_rn(-kPreHi, xm, x0));
+        const float y1 = __fmaf_rn(-kPreLo, x0, __fmaf_rn(-kPreHi, x0, x1));
+        z = make_float2(__fmul_rn(y0, s_win[n]), __fmul_rn(y1, s_win[n + 1]));
+      }
+      X[(2 * slot) * M + m] = z;
+      X[(2 * slot + 1) * M + m] = cmul(z, s_twW[m]);
+    }
+    __syncthreads();
+
+    // ---- the four M-point FFTs ----------------------------------------------
+    float2* x = X;
+    float2* y = Y;
+    {
+      int n = M, st = 1;
+      for (int f = 0; f < p.n_factors; f++) {
+        const int R = p.factors[f];
+        const int m = n / R;
+        const int per = M / R;  // butterflies per transform = m * st
+        for (int b = tid; b < 4 * per; b += THREADS) {
+          const int which = b / per;
+          const int idx = b - which * per;
+          const int pp = idx / st, q = idx - pp * st;
+          const float2* xi = x + which * M;
+          float2* yo = y + which * M;
+          switch (R) {
+            case 8: butterfly<8>(xi, yo, s_twM, M, m, st, pp, q); break;
+            case 5: butterfly<5>(xi, yo, s_twM, M, m, st, pp, q); break;
+            case 4: butterfly<4>(xi, yo, s_twM, M, m, st, pp, q); break;
+            case 3: butterfly<3>(xi, yo, s_twM, M, m, st, pp, q); break;
+            case 2: butterfly<2>(xi, yo, s_twM, M, m, st, pp, q); break;
+            default: butterfly_any(R, xi, yo, s_twM, M, m, st, pp, q); break;
+          }
+        }
+        __syncthreads();
+        float2* tmp = x; x = y; y = tmp;
+        n = m;
+        st *= R;
+      }
+    }
+    // Z[t] of slot: x[(2 slot + (t & 1)) M + (t >> 1)]
+
+    // ---- real-FFT split, power, energy (as in the 16 kHz kernel) -------------
+    float e0 = 0.0f, e1 = 0.0f, mx0 = 0.0f, mx1 = 0.0f;
+    for (int i = tid; i < 2 * (HW - 1); i += THREADS) {
+      const int slot = i >= HW - 1 ? 1 : 0;
+      const int t = 1 + i - slot * (HW - 1);
+      const int k = kk + slot;
+      const float2* Z = x + 2 * slot * M;
+      const int u = W - t;
+      const float2 zk = Z[(t & 1) * M + (t >> 1)], zm = Z[(u & 1) * M + (u >> 1)];
+      const float sx = 0.5f * (zk.x + zm.x), sy = 0.5f * (zk.y - zm.y);
+      const float dx = 0.5f * (zk.x - zm.x), dy = 0.5f * (zk.y + zm.y);
+      const float2 w = s_twN[t];
+      const float px = w.x * dx - w.y * dy, py = w.x * dy + w.y * dx;
+      const float re0 = sx + py, im0 = sy - px;  // X[t]
+      const float re1 = sx - py, im1 = sy + px;  // X[W-t] up to the sign of im
+      const float p0 = __fadd_rn(__fmul_rn(re0, re0), __fmul_rn(im0, im0));
+      const float p1 = __fadd_rn(__fmul_rn(re1, re1), __fmul_rn(im1, im1));
+      float* lm = lmag + (slot == 0 ? ia : ib) * W;
+      lm[t] = __log2f(p0);
+      lm[u] = __log2f(p1);
+      if (slot == 0) { e0 += p0 + p1; mx0 = fmaxf(mx0, fmaxf(p0, p1)); }
+      else { e1 += p0 + p1; mx1 = fmaxf(mx1, fmaxf(p0, p1)); }
+      if (p.tap_spec && k >= k0 && k < k1) {
+        float* tap = p.tap_spec + ((size_t)s * p.tap_stride + (k - kA)) * N;
+        const float m0 = __fsqrt_rn(p0), m1 = __fsqrt_rn(p1);
+        tap[t] = m0;
+        tap[N - t] = m0;
+        tap[u] = m1;
+        tap[N - u] = m1;
+      }
+    }
+    if (tid == 0 || tid == 32) {
+      // bins 0, N/4 and N/2: X[0] = Re Z0 + Im Z0, X[N/2] = Re Z0 - Im Z0,
+      // X[N/4] = conj(Z[W/2]) (W_N^(N/4) = -i)
+      const int slot = tid == 0 ? 0 : 1;
+      const int k = kk + slot;
+      const float2* Z = x + 2 * slot * M;
+      const float2 z0 = Z[0], zq = Z[(HW & 1) * M + (HW >> 1)];
+      const float x0 = z0.x + z0.y;
+      const float p0 = __fmul_rn(x0, x0);
+      const float pq = __fadd_rn(__fmul_rn(zq.x, zq.x), __fmul_rn(zq.y, zq.y));
+      float* lm = lmag + (slot == 0 ? ia : ib) * W;
+      lm[0] = __log2f(p0);
+      lm[HW] = __log2f(pq);
+      if (slot == 0) { e0 += pq; mx0 = fmaxf(mx0, pq); }
+      else { e1 += pq; mx1 = fmaxf(mx1, pq); }
+      if (p.tap_spec && k >= k0 && k < k1) {
+        float* tap = p.tap_spec + ((size_t)s * p.tap_stride + (k - kA)) * N;
+        tap[0] = fabsf(x0);
+        tap[W] = fabsf(z0.x - z0.y);
+        const float mq = __fsqrt_rn(pq);
+        tap[HW] = mq;
+        tap[N - HW] = mq;
+      }
+    }
+    e0 = warp_sum(e0);
+    e1 = warp_sum(e1);
+    mx0 = warp_max(mx0);
+    mx1 = warp_max(mx1);
+    if (lane == 0) {
+      red[warp * 4 + 0] = e0;
+      red[warp * 4 + 1] = e1;
+      red[warp * 4 + 2] = mx0;
+      red[warp * 4 + 3] = mx1;
+    }
+    __syncthreads();
+    float e_slot[2] = {0.0f, 0.0f}, pmax_slot[2] = {0.0f, 0.0f};
+#pragma unroll
+    for (int w = 0; w < NWARP; w++) {
+      e_slot[0] += red[w * 4 + 0];
+      e_slot[1] += red[w * 4 + 1];
+      pmax_slot[0] = fmaxf(pmax_slot[0], red[w * 4 + 2]);
+      pmax_slot[1] = fmaxf(pmax_slot[1], red[w * 4 + 3]);
+    }
+    __syncthreads();  // red is reused below
+
+    // ---- spectral difference against the previous window (log2 domain) -------
+    float linv_slot[2];
+    linv_slot[0] = -__log2f(__fsqrt_rn(e_slot[0]) + 2.2204e-16f);
+    linv_slot[1] = -__log2f(__fsqrt_rn(e_slot[1]) + 2.2204e-16f);
+    const float thr0 = __log2f(pmax_slot[0]) - 13.287712379549449f;  // log2(1e4)
+    const float thr1 = __log2f(pmax_slot[1]) - 13.287712379549449f;
+    const float d20 = 2.0f * (linv_slot[0] - linv_prev);
+    const float d21 = 2.0f * (linv_slot[1] - linv_slot[0]);
+    float acc0 = 0.0f, acc1 = 0.0f;
+    for (int i = tid; i < 2 * (W - 1); i += THREADS) {
+      const int slot = i >= W - 1 ? 1 : 0;
+      const int bin = 1 + i - slot * (W - 1);
+      const float c = lmag[(slot == 0 ? ia : ib) * W + bin];
+      const float l = lmag[(slot == 0 ? ip : ia) * W + bin];
+      if (slot == 0) {
+        if (c > thr0 && l > thr0) acc0 += fabsf((c - l) + d20);
+      } else {
+        if (c > thr1 && l > thr1) acc1 += fabsf((c - l) + d21);
+      }
+    }
+    acc0 = warp_sum(acc0);
+    acc1 = warp_sum(acc1);
+    if (lane == 0) {
+      red[warp * 4 + 0] = acc0;
+      red[warp * 4 + 1] = acc1;
+    }
+    __syncthreads();
+    if (tid < 2) {
+      const int slot = tid;
+      const int k = kk + slot;
+      if (k >= k0 && k < k1) {
+        float t = 0.0f;
+        for (int w = 0; w < NWARP; w++) t += red[w * 4 + slot];
+        p.feat[(size_t)s * p.feat_stride + (k - kA)] = make_float2(e_slot[slot], t * 0.34657359027997264f);  // ln2 / 2
+      }
+    }
+    linv_prev = linv_slot[1];
+    int t = ip; ip = ib; ib = ia; ia = t;  // slot B becomes "previous"
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------
 // Generic path: any N = 2W whose prime factors are small.  One CTA per run.
 // ---------------------------------------------------------------------------
 template <int THREADS>
@@ -549,16 +843,45 @@ cudaError_t launch_k1(const K1Params& p, cudaStream_t stream) {
     k1_spectral_480<WARPS><<<blocks, WARPS * 32, smem, stream>>>(q);
   } else {
     constexpr int THREADS = 128;
-    const int N = p.g.fft;
-    const size_t smem = 2 * (size_t)N * sizeof(float2) + (size_t)N * sizeof(float) + 64 * sizeof(float);
-    static int attr_smem = 0;
-    if ((int)smem > attr_smem) {
-      cudaError_t e = cudaFuncSetAttribute(k1_spectral_generic<THREADS>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return e;
-      attr_smem = (int)smem;
+    const int N = p.g.fft, W = p.g.window, M = W / 2;
+    // radix plan for the M-point transforms: 8, 4, 5, 3, 2, then odd primes up to 16
+    int plan[kMaxFactors], np = 0, rest = M;
+    bool mixed = (W % 2 == 0) && M >= 4 && !getenv("SPEEDY_K1_GENERIC");
+    if (mixed) {
+      const int pref[] = {8, 4, 5, 3, 2, 7, 11, 13};
+      for (int r : pref) {
+        while (rest % r == 0 && np < kMaxFactors) {
+          plan[np++] = r;
+          rest /= r;
+        }
+      }
+      mixed = rest == 1;
     }
-    k1_spectral_generic<THREADS><<<(unsigned)items, THREADS, smem, stream>>>(q);
+    if (mixed) {
+      q.n_factors = np;
+      for (int i = 0; i < np; i++) q.factors[i] = plan[i];
+      const size_t smem = (size_t)(8 * M + 2 * M + W / 2) * sizeof(float2) + (size_t)(4 * W) * sizeof(float) +
+                          (THREADS / 32) * 4 * sizeof(float) +
+                          (size_t)((kRun + 1) * p.g.step + p.g.partial + 16) * sizeof(short);
+      static int attr_smem_m = 0;
+      if ((int)smem > attr_smem_m) {
+        cudaError_t e = cudaFuncSetAttribute(k1_spectral_mixed<THREADS>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_smem_m = (int)smem;
+      }
+      k1_spectral_mixed<THREADS><<<(unsigned)items, THREADS, smem, stream>>>(q);
+    } else {
+      const size_t smem = 2 * (size_t)N * sizeof(float2) + (size_t)N * sizeof(float) + 64 * sizeof(float);
+      static int attr_smem = 0;
+      if ((int)smem > attr_smem) {
+        cudaError_t e = cudaFuncSetAttribute(k1_spectral_generic<THREADS>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_smem = (int)smem;
+      }
+      k1_spectral_generic<THREADS><<<(unsigned)items, THREADS, smem, stream>>>(q);
+    }
   }
   count_launch();
   return cudaGetLastError();
