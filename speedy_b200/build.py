@@ -14,6 +14,7 @@ BUILD = os.environ.get("SPEEDY_B200_BUILD_DIR") or os.path.join(HERE, "_build")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC,-O2,-Wall", "-I" + CSRC]
+COMMON += os.environ.get("SPEEDY_B200_EXTRA_FLAGS", "").split()  # developer A/B builds, e.g. -DK1_RUN=7
 if os.environ.get("SPEEDY_K4_TIMING"):
     COMMON.append("-DK4_TIMING")  # developer build: per-phase cycle counters in k4_sonic
 

@@ -121,10 +121,9 @@ __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+// max over the warp of non-negative floats (their bit patterns order like unsigned integers)
 __device__ __forceinline__ float warp_max(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
+  return __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(v)));
 }
 
 // speedy.c:641-642: inverse_norm = 1.0 / (sqrt(energy) + eps), double, stored float.
@@ -142,6 +141,7 @@ constexpr int P16 = 80;             // window - step
 constexpr int H16 = 240;            // N/2 bins kept
 constexpr int kRun = K1_RUN;        // new windows per warp (plus one halo)
 constexpr int kSampN = (kRun + 1) * S16 + P16;
+static_assert(W16 == 30 * 8 && W16 == S16 + P16, "pass 0 gives eight samples to each of 30 lanes");
 constexpr float kPreHi = 0.97f;                          // speedy.c:422
 constexpr float kPreLo = (float)(0.97 - (double)0.97f);  // remainder of the double constant
 
@@ -213,28 +213,44 @@ __global__ void __launch_bounds__(WARPS * 32) k1_spectral_480(K1Params p) {
 
   // windows are processed in pairs (kk, kk+1), starting at the halo k0-1
   for (int kk = k0 - 1; kk < k1; kk += 2) {
-    // ---- pass 0: int16 -> float, pre-emphasis (double), Hamming ----------
+    // ---- pass 0: int16 -> float, pre-emphasis, Hamming ---------------------
+    // eight consecutive samples per lane (30 lanes x 8 = 240): one 16-byte load of
+    // samples, two of the window table, two 16-byte stores
 #pragma unroll
     for (int slot = 0; slot < 2; slot++) {
       const int k = kk + slot;
       const int o = (k - (k0 - 1)) * S16;
-      float* v = reinterpret_cast<float*>(ws.z[slot]);
+      float4* v4 = reinterpret_cast<float4*>(ws.z[slot]) + 2 * lane;
       const bool live = (k >= 0) && (k < k1);
-      for (int n = lane; n < W16; n += 32) {
-        float out = 0.0f;
+      if (lane < 30) {
+        float4 o0 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), o1 = o0;
         if (live) {
+          const short* sp = ws.samp + o + 8 * lane;
+          const int4 raw = *reinterpret_cast<const int4*>(sp);
           // state entering sample 0 is the last sample of the previous window,
           // i.e. sample P-1 of this one (speedy.c:416-425; window k-1 ends at
           // k*S + P - 1); 0 before the first window.
-          const float xp = (float)((n > 0) ? ws.samp[o + n - 1] : (k >= 1 ? ws.samp[o + P16 - 1] : 0));
-          const float xc = (float)ws.samp[o + n];
+          const float xm = (float)(lane > 0 ? sp[-1] : (k >= 1 ? ws.samp[o + P16 - 1] : 0));
+          const float x0 = (float)(short)(raw.x & 0xffff), x1 = (float)(raw.x >> 16);
+          const float x2 = (float)(short)(raw.y & 0xffff), x3 = (float)(raw.y >> 16);
+          const float x4 = (float)(short)(raw.z & 0xffff), x5 = (float)(raw.z >> 16);
+          const float x6 = (float)(short)(raw.w & 0xffff), x7 = (float)(raw.w >> 16);
+          const float4 w0 = *reinterpret_cast<const float4*>(s_win + 8 * lane);
+          const float4 w1 = *reinterpret_cast<const float4*>(s_win + 8 * lane + 4);
           // y = x - 0.97 * state (speedy.c:422, evaluated there in double): 0.97 is
           // split into a float and its remainder so the constant carries no error;
           // the /32768 of speedy.c:558 is folded into the window table.
-          const float y = __fmaf_rn(-kPreLo, xp, __fmaf_rn(-kPreHi, xp, xc));
-          out = __fmul_rn(y, s_win[n]);
+          o0.x = __fmul_rn(__fmaf_rn(-kPreLo, xm, __fmaf_rn(-kPreHi, xm, x0)), w0.x);
+          o0.y = __fmul_rn(__fmaf_rn(-kPreLo, x0, __fmaf_rn(-kPreHi, x0, x1)), w0.y);
+          o0.z = __fmul_rn(__fmaf_rn(-kPreLo, x1, __fmaf_rn(-kPreHi, x1, x2)), w0.z);
+          o0.w = __fmul_rn(__fmaf_rn(-kPreLo, x2, __fmaf_rn(-kPreHi, x2, x3)), w0.w);
+          o1.x = __fmul_rn(__fmaf_rn(-kPreLo, x3, __fmaf_rn(-kPreHi, x3, x4)), w1.x);
+          o1.y = __fmul_rn(__fmaf_rn(-kPreLo, x4, __fmaf_rn(-kPreHi, x4, x5)), w1.y);
+          o1.z = __fmul_rn(__fmaf_rn(-kPreLo, x5, __fmaf_rn(-kPreHi, x5, x6)), w1.z);
+          o1.w = __fmul_rn(__fmaf_rn(-kPreLo, x6, __fmaf_rn(-kPreHi, x6, x7)), w1.w);
         }
-        v[n] = out;
+        v4[0] = o0;
+        v4[1] = o1;
       }
     }
     __syncwarp();
@@ -365,9 +381,13 @@ __global__ void __launch_bounds__(WARPS * 32) k1_spectral_480(K1Params p) {
         const float thr = __log2f(pmax_slot[slot]) - 13.287712379549449f;  // log2(1e4)
         const float d2 = 2.0f * (linv_slot[slot] - linv_last);
         float acc = 0.0f;
-        for (int i = 1 + lane; i < H16; i += 32) {
-          const float c = lc[i], l = ll[i];
-          if (c > thr && l > thr) acc += fabsf((c - l) + d2);
+        for (int j = lane; j < H16 / 4; j += 32) {  // bins 4j .. 4j+3, bin 0 excluded
+          const float4 c = *reinterpret_cast<const float4*>(lc + 4 * j);
+          const float4 l = *reinterpret_cast<const float4*>(ll + 4 * j);
+          if (j > 0 && c.x > thr && l.x > thr) acc += fabsf((c.x - l.x) + d2);
+          if (c.y > thr && l.y > thr) acc += fabsf((c.y - l.y) + d2);
+          if (c.z > thr && l.z > thr) acc += fabsf((c.z - l.z) + d2);
+          if (c.w > thr && l.w > thr) acc += fabsf((c.w - l.w) + d2);
         }
         const float lsd = warp_sum(acc) * 0.34657359027997264f;  // ln2 / 2
         const int j = k - kA;

@@ -820,6 +820,7 @@ cudaError_t launch_k4(const K4Params& p0, cudaStream_t stream) {
   if (const char* e = getenv("SPEEDY_K4_THREADS")) t = atoi(e);
   if (t == 0) t = 32;  // measured: extra warps do not shorten the chain enough to pay for their barriers
   if (t <= 32) {
+    if (p.n_streams > 148 * 16) return launch_k4_t<1, 20>(p, stream);
     return p.n_streams > 148 * 12 ? launch_k4_t<1, 16>(p, stream) : launch_k4_t<1, 1>(p, stream);
   }
   if (t <= 64) return launch_k4_t<2, 7>(p, stream);
