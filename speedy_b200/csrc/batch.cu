@@ -917,12 +917,45 @@ int speedyBatchProcess(speedyBatch b, const int16_t* h_in, int64_t frames, int16
   }
   CU_TRY(cudaSetDevice(b->cfg.device));
   const int n = b->n, C = b->g.channels;
-  long long chunk = (frames + 11) / 12;
-  if (const char* e = getenv("SPEEDY_B200_CHUNK_FRAMES")) chunk = atoll(e) > 0 ? atoll(e) : chunk;
-  if (chunk < 4 * b->g.rate / 10) chunk = 4 * b->g.rate / 10;  // at least 0.4 s of audio
+  // Chunk boundaries.  The kernels outrun PCIe, so what the call adds to the transfer
+  // time is the work left when the last byte lands: the last chunks taper off
+  // (..., 1, 1, 0.8, 0.6, 0.4, 0.2 of the regular size) to keep that tail short.
+  long long chunk = (frames + 9) / 10;
+  bool taper = true;
+  if (const char* e = getenv("SPEEDY_B200_CHUNK_FRAMES")) {
+    if (atoll(e) > 0) {
+      chunk = atoll(e);
+      taper = false;
+    }
+  }
+  const long long min_chunk = 4 * b->g.rate / 10;  // at least 0.4 s of audio
+  if (chunk < min_chunk) chunk = min_chunk;
   chunk = (chunk + 7) & ~7LL;
   if (chunk > frames) chunk = frames;
-  const int nchunks = (int)((frames + chunk - 1) / chunk);
+  std::vector<long long> bound(1, 0);
+  {
+    long long at = 0;
+    const double tail[4] = {0.8, 0.6, 0.4, 0.2};
+    const long long tapered = taper ? 2 * chunk : 0;  // the four tapered chunks cover two regular ones
+    while (at < frames) {
+      long long next = at + chunk;
+      if (taper && frames - at <= tapered + 8 && frames - at > min_chunk * 4) {
+        const long long left = frames - at;
+        for (int i = 0; i < 4 && at < frames; i++) {
+          long long sz = ((long long)(left * tail[i] / 2.0) + 7) & ~7LL;
+          if (sz < min_chunk) sz = min_chunk;
+          next = i == 3 || at + sz > frames ? (long long)frames : at + sz;
+          bound.push_back(next);
+          at = next;
+        }
+        break;
+      }
+      if (next > frames) next = frames;
+      bound.push_back(next);
+      at = next;
+    }
+  }
+  const int nchunks = (int)bound.size() - 1;
   if (!ensure_stage(b, frames) || !ensure_aux_streams(b)) return 0;
   if (!b->pipe_ready) {
     int prio_lo = 0, prio_hi = 0;
@@ -1007,16 +1040,16 @@ int speedyBatchProcess(speedyBatch b, const int16_t* h_in, int64_t frames, int16
   };
   // all host->device copies are queued up front: the copy stream never runs dry
   for (int c = 0; c < nchunks; c++) {
-    const long long f0 = (long long)c * chunk;
-    const long long fc = frames - f0 < chunk ? frames - f0 : chunk;
+    const long long f0 = bound[c];
+    const long long fc = bound[c + 1] - f0;
     CU_TRY(cudaMemcpy2DAsync(b->d_stage + f0 * C, stage_pitch, h_in + f0 * C, in_pitch,
                              (size_t)fc * C * sizeof(int16_t), n, cudaMemcpyHostToDevice, b->s_h2d));
     CU_TRY(cudaEventRecord(ev_in[c], b->s_h2d));
   }
   WriteCall w = {b, b->d_stage, b->stage_frames, frames, nullptr};
   for (int c = 0; c < nchunks && ok; c++) {
-    const long long done = (long long)c * chunk;
-    const long long prefix = done + chunk < frames ? done + chunk : (long long)frames;
+    const long long done = bound[c];
+    const long long prefix = bound[c + 1];
     CU_TRY(cudaStreamWaitEvent(sa, ev_in[c], 0));
     if (!launch_analysis(w, done, prefix, sa)) ok = 0;
     CU_TRY(cudaEventRecord(ev_k2[c], sa));
