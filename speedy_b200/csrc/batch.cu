@@ -336,7 +336,8 @@ int64_t speedyBatchKernelLaunches(void) { return g_launches.load(); }
 
 const char* speedyBatchBuildInfo(void) {
   return "speedy_b200 sm_100a: k1_spectral_480<4 warps> (radix-8 x radix-15 real FFT) | "
-         "k1_spectral_generic<128> | k2_tension | k4_sonic<32|64|128> | tail | read | synth";
+         "k1_spectral_mixed<128> (packed half-length Stockham FFT, any even window) | k1_spectral_generic<128> | "
+         "k2_tension | k4_sonic<1|2|4 warps per stream, mono specialisation> | tail | read | synth";
 }
 
 void speedyBatchDefaultConfig(speedyBatchConfig* cfg) {

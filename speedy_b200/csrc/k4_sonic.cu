@@ -68,11 +68,11 @@ template <int NW, int CH>
 struct Sonic {
   static constexpr int VL = 32 * NW;  // lanes cooperating on one stream
   // geometry
-  int Crt, S, minP, maxP, maxReq, skip;
+  int Crt, S, minP, maxP, maxReq, skip;  // Crt: channel count when not a template constant
   long long cap;
   // shared memory (this warp's slice)
   int* w32;                 // mono window, 32-bit [bufN + kPad]
-  short* buf;               // interleaved raw window ((CH ? CH : Crt) > 1 only) [bufN * (CH ? CH : Crt)]
+  short* buf;               // interleaved raw window (C > 1 only) [bufN * C]
   int* ds32;                // decimated mono [maxReq / skip + kPad]
   int bufN;
   // window state (warp-uniform)
@@ -95,6 +95,9 @@ struct Sonic {
   unsigned dec_magic;
   bool timing;
 
+  // channel count: a compile-time constant in the mono specialisation (CH = 1)
+  __device__ __forceinline__ int nch() const { return CH ? CH : Crt; }
+
   // Make [start, start + count) resident in the shared window (count <= bufN - 8).
   __device__ __forceinline__ void sync() {
     if (NW == 1) __syncwarp(); else __syncthreads();
@@ -106,7 +109,7 @@ struct Sonic {
     sync();  // every lane is done with the old window
     bufStart = start & ~7LL;  // keeps the 16-byte loads of the refill aligned
     bufLen = bufN;
-    stage_mono<VL, int>(src, bufStart, bufN, zero_from, w32, (CH ? CH : Crt) > 1 ? buf : nullptr, vl);
+    stage_mono<VL, int>(src, bufStart, bufN, zero_from, w32, nch() > 1 ? buf : nullptr, vl);
     sync();
     T_END(0);
   }
@@ -124,17 +127,17 @@ struct Sonic {
   // Append n frames starting at absolute frame `from` to the output.
   __device__ __forceinline__ void emit_copy(long long from, int n, int out_offset_frames) {
     const int o0 = (int)(from - bufStart);
-    const int total = n * (CH ? CH : Crt);
-    const long long base = (long long)(outCount + out_offset_frames) * (CH ? CH : Crt);
-    const long long room = cap * (CH ? CH : Crt) - base;
+    const int total = n * nch();
+    const long long base = (long long)(outCount + out_offset_frames) * nch();
+    const long long room = cap * nch() - base;
     short* o = out + base;
     T_BEGIN();
-    if ((CH ? CH : Crt) == 1) {
+    if (nch() == 1) {
       for (int i = vl; i < total; i += VL) {
         if (i < room) o[i] = (short)w32[o0 + i];
       }
     } else {
-      const short* p = buf + (size_t)o0 * (CH ? CH : Crt);
+      const short* p = buf + (size_t)o0 * nch();
       for (int i = vl; i < total; i += VL) {
         if (i < room) o[i] = p[i];
       }
@@ -155,13 +158,13 @@ struct Sonic {
     return num < 0 ? -q : q;
   }
 
-  // out[t] = (down[t]*(n-t) + up[t]*t) / n per channel, (CH ? CH : Crt) integer arithmetic.
+  // out[t] = (down[t]*(n-t) + up[t]*t) / n per channel, C integer arithmetic.
   // down/up are absolute frames inside the window.
   __device__ __forceinline__ void overlap_add(int n, long long down, long long up, int out_offset_frames) {
     const int d0 = (int)(down - bufStart), u0 = (int)(up - bufStart);
-    const int total = n * (CH ? CH : Crt);
-    const long long base = (long long)(outCount + out_offset_frames) * (CH ? CH : Crt);
-    const long long room = cap * (CH ? CH : Crt) - base;
+    const int total = n * nch();
+    const long long base = (long long)(outCount + out_offset_frames) * nch();
+    const long long room = cap * nch() - base;
     short* o = out + base;
     T_BEGIN();
     // trunc(|num| / n) == umulhi(|num|, magic) >> shift for |num| < 2^25, 1 < n < 2^11,
@@ -173,7 +176,7 @@ struct Sonic {
       const double qd = __ddiv_rn((double)(1ULL << (32 + shift)), (double)n);
       magic = (unsigned)(unsigned long long)qd + ((n & (n - 1)) ? 1u : 0u);
     }
-    if ((CH ? CH : Crt) == 1) {
+    if (nch() == 1) {
       if (n == 1) {
         if (vl == 0 && 0 < room) o[0] = (short)w32[d0];
       } else {
@@ -184,10 +187,10 @@ struct Sonic {
         }
       }
     } else {
-      const short* dp = buf + (size_t)d0 * (CH ? CH : Crt);
-      const short* up_ = buf + (size_t)u0 * (CH ? CH : Crt);
+      const short* dp = buf + (size_t)d0 * nch();
+      const short* up_ = buf + (size_t)u0 * nch();
       for (int i = vl; i < total; i += VL) {
-        int t = i / (CH ? CH : Crt);
+        int t = i / nch();
         const int num = (int)dp[i] * (n - t) + (int)up_[i] * t;
         const int q = n == 1 ? abs(num) : (int)(__umulhi((unsigned)abs(num), magic) >> shift);
         if (i < room) o[i] = (short)(num < 0 ? -q : q);
@@ -196,14 +199,14 @@ struct Sonic {
     T_END(6);
   }
 
-  // Upstream downSampleInput: sum `skip` frames x (CH ? CH : Crt) channels, (CH ? CH : Crt) integer division
+  // Upstream downSampleInput: sum `skip` frames x C channels, C integer division
   // (truncating).  |sum| < 2^21 and the divisor is small, so the quotient is exact
   // as (|sum| * ceil(2^32 / divisor)) >> 32.
   __device__ __forceinline__ void decimate(int off) {
     T_BEGIN();
     const int count = maxReq / skip;
-    const int per = (CH ? CH : Crt) * skip;
-    if ((CH ? CH : Crt) == 1 && (skip & 3) == 0) {
+    const int per = nch() * skip;
+    if (nch() == 1 && (skip & 3) == 0) {
       const int r = off & 3;
       const int nmid = (skip >> 2) - 1;
       const int* base = w32 + (off & ~3);
@@ -225,12 +228,12 @@ struct Sonic {
 #pragma unroll 1
       for (int i = vl; i < count; i += VL) {
         int v = 0;
-        if ((CH ? CH : Crt) == 1) {
+        if (nch() == 1) {
           const int* q = w32 + off + i * skip;
 #pragma unroll 1
           for (int j = 0; j < skip; j++) v += q[j];
         } else {
-          const short* q = buf + ((size_t)off + (size_t)i * skip) * (CH ? CH : Crt);
+          const short* q = buf + ((size_t)off + (size_t)i * skip) * nch();
           int j = 0;
 #pragma unroll 1
           for (; j + 4 <= per; j += 4) v += (q[j] + q[j + 1]) + (q[j + 2] + q[j + 3]);
@@ -281,7 +284,7 @@ struct Sonic {
   }
 
   // Exact arg-min and arg-max of diff/period over the warp's candidates (one
-  // (diff, period) pair per lane for each, period 0 = none).  The (CH ? CH : Crt) scan compares by
+  // (diff, period) pair per lane for each, period 0 = none).  The C scan compares by
   // cross-multiplication with strict inequalities, so ties go to the smaller lag.
   // A float quotient picks the lanes within 2e-6 of the extremum (a superset of the
   // true extremum: its relative error is below 4e-7); almost always that is one
@@ -334,7 +337,7 @@ struct Sonic {
   }
 
   // Fold the four lag sums a lane holds (lags pg .. pg+3) into its running best /
-  // worst candidates; lags ascend, so strict comparisons reproduce the (CH ? CH : Crt) scan.
+  // worst candidates; lags ascend, so strict comparisons reproduce the C scan.
   __device__ __forceinline__ void fold(const unsigned (&d)[4], int pg, int lo, int hi, unsigned& bd, int& bp,
                                        unsigned& wd, int& wp) {
 #pragma unroll
@@ -451,7 +454,7 @@ struct Sonic {
     unsigned best_diff, worst_diff;
     int best, worst;
     pick2(bd, bp, wd, wp, &best_diff, &best, &worst_diff, &worst);
-    // the (CH ? CH : Crt) scan starts from (maxDiff = 0, worstPeriod = 255) and only replaces
+    // the C scan starts from (maxDiff = 0, worstPeriod = 255) and only replaces
     // it with a strictly larger ratio
     if (worst_diff == 0u) worst = 255;
     *minDiff = udiv_small(best_diff, best);
@@ -468,7 +471,7 @@ struct Sonic {
     const int* arr = w32;
     int aoff = off;
     int lo = minP, hi = maxP, stages = 1;
-    if (!((CH ? CH : Crt) == 1 && skip == 1)) {
+    if (!(nch() == 1 && skip == 1)) {
       decimate(off);
       arr = ds32;
       aoff = 0;
