@@ -44,6 +44,9 @@ METRICS = {
 
 def main():
     tag, rep, launches, *bench = sys.argv[1:]
+    command = os.environ.get("SUMMARIZE_COMMAND") or (
+        "SPEEDY_B200_WRITE_PARTS=1 ncu --set full --clock-control none --import-source on "
+        "-k regex:'k4_sonic|k1_spectral|k2_tension' --launch-skip 12 --launch-count 4 python bench.py --steps 1 --warmup 3")
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
@@ -59,9 +62,11 @@ def main():
                     k[name] = r[ix[m]]
                 k[name + "_unit"] = units[ix[m]]
         kernels.append(k)
-    json.dump({"source": os.path.basename(rep), "command": "ncu --set full --clock-control none --import-source on "
-               "-k regex:'k4_sonic|k1_spectral|k2_tension' -s 3 -c 3 python bench.py --steps 1 --warmup 3",
-               "kernels": kernels}, open(os.path.join(HERE, tag + "_kernels.json"), "w"), indent=1)
+    json.dump({"source": os.path.basename(rep), "command": command, "kernels": kernels},
+              open(os.path.join(HERE, tag + "_kernels.json"), "w"), indent=1)
+    if launches == "-":  # a kernel capture only
+        print(json.dumps([{k: v for k, v in kk.items() if not k.endswith("_unit")} for kk in kernels], indent=1)[:3000])
+        return
     # launch list
     lines = [l for l in open(launches) if not l.startswith("==")]
     rows = list(csv.reader(io.StringIO("".join(lines))))
@@ -82,7 +87,7 @@ def main():
         for i, name, ms in out:
             f.write('%s,"%s",%.6f\n' % (i, name, ms))
     total = sum(share.values())
-    json.dump({"command": "ncu --metrics gpu__time_duration.sum --clock-control none -c 400 python bench.py "
+    json.dump({"command": "ncu --metrics gpu__time_duration.sum --clock-control none -c 600 python bench.py "
                "--steps 2 --warmup 3 (cold-cache, serialised: compare shares, not absolutes)",
                "total_ms": total,
                "share": {k: {"ms": v, "frac": v / total} for k, v in sorted(share.items(), key=lambda kv: -kv[1])}},

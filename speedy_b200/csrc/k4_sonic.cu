@@ -789,8 +789,19 @@ static int k4_buf_frames(const Geometry& g, int n_streams) {
   int n = (n_streams >= 148 * 12 ? 4 : 8) * g.max_required;
   const int floor_n = n_streams >= 148 * 12 ? 2048 : 4096;
   if (n < floor_n) n = floor_n;
+  // ... but never so large that the streams of one wave stop fitting on their SM: the
+  // splice chain is latency bound, a second wave of CTAs would double the run time
+  // (48 kHz stereo: 8 search spans are 95 KB per stream)
+  int ctas = (n_streams + 147) / 148;
+  if (ctas > 20) ctas = 20;
+  const long long budget = (227LL * 1024) / ctas - 1024;  // per CTA, 1 KB reserved by the system
+  const long long per_frame = sizeof(int) + (g.channels > 1 ? g.channels * sizeof(short) : 0);
+  const long long fit = ((long long)budget - (long long)k4_stream_smem(g, 0)) / per_frame;
+  if (n > fit) n = (int)fit;
+  const int least = g.max_required + g.max_required / 2;  // one search span plus room to slide
+  if (n < least) n = least;
   if (const char* e = getenv("SPEEDY_K4_BUF")) n = atoi(e) > 2 * g.max_required ? atoi(e) : n;
-  return (n + 63) & ~63;
+  return n & ~63;
 }
 
 template <int NW, int MINB, int CH>
