@@ -444,6 +444,54 @@ __device__ __forceinline__ void butterfly(const float2* x, float2* y, const floa
   for (int t = 1; t < R; t++) y[q + st * (R * pp + t)] = cmul(a[t], twM[tstep * t]);
 }
 
+// Odd prime radix R (7, 11, 13) in registers: with S_r = a_r + a_{R-r}, D_r = a_r - a_{R-r},
+//   y_t, y_{R-t} = (a_0 + sum_r S_r cos(2 pi r t / R))  -/+  i sum_r D_r sin(2 pi r t / R),
+// r, t = 1 .. (R-1)/2, which halves the multiplications of the direct form.
+template <int R>
+__device__ __forceinline__ void butterfly_prime(const float2* x, float2* y, const float2* twM, int M, int m, int st,
+                                                int pp, int q) {
+  constexpr int H = (R - 1) / 2;
+  float2 a[R];
+#pragma unroll
+  for (int r = 0; r < R; r++) a[r] = x[q + st * (pp + r * m)];
+  float c[H + 1], sn[H + 1];
+  const int wr = M / R;
+#pragma unroll
+  for (int j = 1; j <= H; j++) {
+    const float2 w = twM[wr * j];  // (cos, -sin)(2 pi j / R)
+    c[j] = w.x;
+    sn[j] = -w.y;
+  }
+  float2 S[H + 1], D[H + 1];
+  float2 y0 = a[0];
+#pragma unroll
+  for (int r = 1; r <= H; r++) {
+    S[r] = cadd(a[r], a[R - r]);
+    D[r] = csub(a[r], a[R - r]);
+    y0 = cadd(y0, S[r]);
+  }
+  const int tstep = st * pp;
+  y[q + st * (R * pp)] = y0;
+#pragma unroll
+  for (int t = 1; t <= H; t++) {
+    float2 P = a[0], Q = make_float2(0.0f, 0.0f);
+#pragma unroll
+    for (int r = 1; r <= H; r++) {
+      const int e = (r * t) % R;
+      const float cc = e <= H ? c[e] : c[R - e];
+      const float ss = e <= H ? sn[e] : -sn[R - e];
+      P.x = fmaf(S[r].x, cc, P.x);
+      P.y = fmaf(S[r].y, cc, P.y);
+      Q.x = fmaf(D[r].x, ss, Q.x);
+      Q.y = fmaf(D[r].y, ss, Q.y);
+    }
+    const float2 yt = make_float2(P.x + Q.y, P.y - Q.x);   // P - i Q
+    const float2 yr = make_float2(P.x - Q.y, P.y + Q.x);   // P + i Q
+    y[q + st * (R * pp + t)] = cmul(yt, twM[tstep * t]);
+    y[q + st * (R * pp + R - t)] = cmul(yr, twM[tstep * (R - t)]);
+  }
+}
+
 // Any other (odd prime) radix up to 16: direct O(R^2) butterfly.
 __device__ __forceinline__ void butterfly_any(int R, const float2* x, float2* y, const float2* twM, int M, int m,
                                               int st, int pp, int q) {
@@ -547,15 +595,17 @@ __global__ void __launch_bounds__(THREADS) k1_spectral_mixed(K1Params p) {
     float2* x = X;
     float2* y = Y;
     {
-      int n = M, st = 1;
+      int st = 1;
       for (int f = 0; f < p.n_factors; f++) {
         const int R = p.factors[f];
-        const int m = n / R;
-        const int per = M / R;  // butterflies per transform = m * st
+        const int m = p.plan_m[f];      // sub-transform length after this stage: n / R
+        const int per = p.plan_per[f];  // butterflies per transform = M / R = m * st
+        // floor(a / b) == int((a + 0.5) / b) in float for these small integers
+        const float rcp_per = __frcp_rn((float)per), rcp_st = __frcp_rn((float)st);
         for (int b = tid; b < 4 * per; b += THREADS) {
-          const int which = b / per;
+          const int which = (int)(((float)b + 0.5f) * rcp_per);
           const int idx = b - which * per;
-          const int pp = idx / st, q = idx - pp * st;
+          const int pp = (int)(((float)idx + 0.5f) * rcp_st), q = idx - pp * st;
           const float2* xi = x + which * M;
           float2* yo = y + which * M;
           switch (R) {
@@ -564,12 +614,14 @@ __global__ void __launch_bounds__(THREADS) k1_spectral_mixed(K1Params p) {
             case 4: butterfly<4>(xi, yo, s_twM, M, m, st, pp, q); break;
             case 3: butterfly<3>(xi, yo, s_twM, M, m, st, pp, q); break;
             case 2: butterfly<2>(xi, yo, s_twM, M, m, st, pp, q); break;
+            case 7: butterfly_prime<7>(xi, yo, s_twM, M, m, st, pp, q); break;
+            case 11: butterfly_prime<11>(xi, yo, s_twM, M, m, st, pp, q); break;
+            case 13: butterfly_prime<13>(xi, yo, s_twM, M, m, st, pp, q); break;
             default: butterfly_any(R, xi, yo, s_twM, M, m, st, pp, q); break;
           }
         }
         __syncthreads();
         float2* tmp = x; x = y; y = tmp;
-        n = m;
         st *= R;
       }
     }
@@ -660,15 +712,38 @@ __global__ void __launch_bounds__(THREADS) k1_spectral_mixed(K1Params p) {
     const float d20 = 2.0f * (linv_slot[0] - linv_prev);
     const float d21 = 2.0f * (linv_slot[1] - linv_slot[0]);
     float acc0 = 0.0f, acc1 = 0.0f;
-    for (int i = tid; i < 2 * (W - 1); i += THREADS) {
-      const int slot = i >= W - 1 ? 1 : 0;
-      const int bin = 1 + i - slot * (W - 1);
-      const float c = lmag[(slot == 0 ? ia : ib) * W + bin];
-      const float l = lmag[(slot == 0 ? ip : ia) * W + bin];
-      if (slot == 0) {
-        if (c > thr0 && l > thr0) acc0 += fabsf((c - l) + d20);
+    {
+      // bins 1 .. W-1 of both slots, four per 16-byte load (W is a multiple of 4 here,
+      // otherwise one at a time)
+      const float* ca = lmag + ia * W;
+      const float* cb = lmag + ib * W;
+      const float* la = lmag + ip * W;
+      if ((W & 3) == 0) {
+        const int nv = W >> 2;
+        for (int i = tid; i < 2 * nv; i += THREADS) {
+          const int slot = i >= nv ? 1 : 0;
+          const int j = i - slot * nv;
+          const float4 c = *reinterpret_cast<const float4*>((slot ? cb : ca) + 4 * j);
+          const float4 l = *reinterpret_cast<const float4*>((slot ? ca : la) + 4 * j);
+          const float thr = slot ? thr1 : thr0, d2 = slot ? d21 : d20;
+          float a = 0.0f;
+          if (j > 0 && c.x > thr && l.x > thr) a += fabsf((c.x - l.x) + d2);
+          if (c.y > thr && l.y > thr) a += fabsf((c.y - l.y) + d2);
+          if (c.z > thr && l.z > thr) a += fabsf((c.z - l.z) + d2);
+          if (c.w > thr && l.w > thr) a += fabsf((c.w - l.w) + d2);
+          if (slot) acc1 += a; else acc0 += a;
+        }
       } else {
-        if (c > thr1 && l > thr1) acc1 += fabsf((c - l) + d21);
+        for (int i = tid; i < 2 * (W - 1); i += THREADS) {
+          const int slot = i >= W - 1 ? 1 : 0;
+          const int bin = 1 + i - slot * (W - 1);
+          const float c = (slot ? cb : ca)[bin], l = (slot ? ca : la)[bin];
+          if (slot == 0) {
+            if (c > thr0 && l > thr0) acc0 += fabsf((c - l) + d20);
+          } else {
+            if (c > thr1 && l > thr1) acc1 += fabsf((c - l) + d21);
+          }
+        }
       }
     }
     acc0 = warp_sum(acc0);
@@ -879,7 +954,12 @@ cudaError_t launch_k1(const K1Params& p, cudaStream_t stream) {
     }
     if (mixed) {
       q.n_factors = np;
-      for (int i = 0; i < np; i++) q.factors[i] = plan[i];
+      for (int i = 0, n = M; i < np; i++) {
+        q.factors[i] = plan[i];
+        n /= plan[i];
+        q.plan_m[i] = n;
+        q.plan_per[i] = M / plan[i];
+      }
       const size_t smem = (size_t)(8 * M + 2 * M + W / 2) * sizeof(float2) + (size_t)(4 * W) * sizeof(float) +
                           (THREADS / 32) * 4 * sizeof(float) +
                           (size_t)((kRun + 1) * p.g.step + p.g.partial + 16) * sizeof(short);

@@ -43,7 +43,9 @@ struct K1Params {
   const float2* tw_n;            // [N] W_N^k
   const float2* tw_half;         // [N/2] W_{N/2}^k
   int n_factors;
-  int factors[kMaxFactors];      // generic path: radices of N
+  int factors[kMaxFactors];      // generic path: radices of N; mixed path: radices of M = W/2
+  int plan_m[kMaxFactors];       // mixed path: sub-transform length after each stage
+  int plan_per[kMaxFactors];     // mixed path: butterflies per transform in each stage
   // optional tap: [n][tap_stride][N]
   float* tap_spec;
   int tap_stride;
