@@ -29,6 +29,7 @@
 #endif
 
 #define ORACLE_MAX_FACTORS 32
+#define ORACLE_MAX_RADIX 2048
 
 static int factorize(int n, int* factors) {
   int count = 0;
@@ -93,7 +94,8 @@ static int factorize(int n, int* factors) {
         const cpx_##SUFFIX* xi = x + q + s * p;                                \
         cpx_##SUFFIX* yo = y + q + s * radix * p;                              \
         const int xs = s * m;                                                  \
-        cpx_##SUFFIX o[64];                                                    \
+        cpx_##SUFFIX o[ORACLE_MAX_RADIX];                                      \
+        o[0].r = 0; o[0].i = 0;                                                \
         if (radix == 2) {                                                      \
           cpx_##SUFFIX a = xi[0], b = xi[xs];                                  \
           o[0].r = a.r + b.r; o[0].i = a.i + b.i;                              \
@@ -110,7 +112,7 @@ static int factorize(int n, int* factors) {
           o[2].r = apc.r - bpd.r;  o[2].i = apc.i - bpd.i;                     \
           o[3].r = amc.r - jbmd.r; o[3].i = amc.i - jbmd.i;                    \
         } else {                                                               \
-          cpx_##SUFFIX a[64];                                                  \
+          cpx_##SUFFIX a[ORACLE_MAX_RADIX]; /* 44.1 kHz: N = 1322 = 2 * 661 */   \
           for (int r = 0; r < radix; r++) a[r] = xi[r * xs];                   \
           for (int t = 0; t < radix; t++) {                                    \
             cpx_##SUFFIX acc = a[0];                                           \

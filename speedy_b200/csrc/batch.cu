@@ -422,7 +422,7 @@ speedyBatch speedyBatchCreate(const speedyBatchConfig* cfg) {
   bool ok = b->n_factors > 0;
   if (!ok) set_error("speedyBatchCreate: unsupported FFT size");
   for (int i = 0; ok && i < b->n_factors; i++) {
-    if (b->factors[i] > 61) {
+    if (b->factors[i] > 2047) {  // the generic kernel loops over the radix: any prime works, slowly
       ok = false;
       set_error("speedyBatchCreate: FFT size has a large prime factor");
     }

@@ -158,7 +158,8 @@ def test_ragged_and_short_inputs():
         assert np.array_equal(outs[s], o2["out"]), (s, len(outs[s]), len(o2["out"]))
 
 
-@pytest.mark.parametrize("rate,channels,speed", [(22050, 1, 3.5), (24000, 1, 2.0), (48000, 2, 1.5), (16000, 2, 3.0)])
+@pytest.mark.parametrize("rate,channels,speed", [(22050, 1, 3.5), (24000, 1, 2.0), (48000, 2, 1.5), (16000, 2, 3.0),
+                                                 (8000, 1, 2.0), (32000, 2, 2.5), (44100, 1, 2.0), (11025, 1, 1.7)])
 def test_other_rates_and_stereo(rate, channels, speed):
     n, frames = 3, rate * 2
     pcm = ol.synth(31, n, rate, channels, frames)
