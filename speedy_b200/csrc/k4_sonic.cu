@@ -204,6 +204,7 @@ struct Sonic {
   // as (|sum| * ceil(2^32 / divisor)) >> 32.
   __device__ __forceinline__ void decimate(int off) {
     T_BEGIN();
+    sync();  // every lane is done reading the previous decimated copy
     const int count = maxReq / skip;
     const int per = nch() * skip;
     if (nch() == 1 && (skip & 3) == 0) {
