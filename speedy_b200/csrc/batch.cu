@@ -216,6 +216,42 @@ static int factorize(int n, int* f) {
   return c;
 }
 
+// Does the mixed-radix spectrogram kernel take this window (k1_spectral.cu: even, and
+// W / 2 a product of 2, 3, 5, 7, 11, 13)?
+static bool mixed_radix_window(int window) {
+  if (window % 2 != 0 || window / 2 < 4) return false;
+  int rest = window / 2;
+  const int pref[] = {2, 3, 5, 7, 11, 13};
+  for (int r : pref) {
+    while (rest % r == 0) rest /= r;
+  }
+  return rest == 1;
+}
+
+// Convolution length for the chirp-z kernel: a 7-smooth L >= n with few radix stages
+// when taken as 8, 4, 5, 3, 2, 7 (cost ~ L x stages).
+static int chirp_length(int n) {
+  int best = 0;
+  long long best_cost = 0;
+  for (int L = n; L <= 2 * n; L++) {
+    int rest = L, stages = 0;
+    const int pref[] = {8, 4, 5, 3, 2, 7};
+    for (int r : pref) {
+      while (rest % r == 0) {
+        rest /= r;
+        stages++;
+      }
+    }
+    if (rest != 1 || stages > kMaxFactors) continue;
+    const long long cost = (long long)L * stages;
+    if (!best || cost < best_cost) {
+      best = L;
+      best_cost = cost;
+    }
+  }
+  return best;
+}
+
 }  // namespace speedy
 
 using namespace speedy;
@@ -233,6 +269,11 @@ struct speedyBatchStruct {
   float2* d_tw_half;
   int n_factors;
   int factors[kMaxFactors];
+  // chirp-z tables (windows the mixed-radix kernel cannot factor, e.g. 44.1 kHz)
+  int bl_L;
+  float2* d_bl_tw;
+  float2* d_bl_B;
+  float2* d_bl_chirp;
   // history (ping-pong)
   int16_t* d_hist[2];
   int hist_cur;
@@ -336,7 +377,8 @@ int64_t speedyBatchKernelLaunches(void) { return g_launches.load(); }
 
 const char* speedyBatchBuildInfo(void) {
   return "speedy_b200 sm_100a: k1_spectral_480<4 warps> (radix-8 x radix-15 real FFT) | "
-         "k1_spectral_mixed<128> (packed half-length Stockham FFT, any even window) | k1_spectral_generic<128> | "
+         "k1_spectral_mixed<128> (packed half-length Stockham FFT, any even window) | k1_spectral_bluestein<128> (chirp-z, "
+         "prime windows) | k1_spectral_generic<128> | "
          "k2_tension | k4_sonic<1|2|4 warps per stream, mono specialisation> | tail | read | synth";
 }
 
@@ -461,6 +503,54 @@ speedyBatch speedyBatchCreate(const speedyBatchConfig* cfg) {
       cudaMemcpy(b->d_window, w.data(), sizeof(float) * g.window, cudaMemcpyHostToDevice);
       cudaMemcpy(b->d_tw_n, tn.data(), sizeof(float2) * g.fft, cudaMemcpyHostToDevice);
       cudaMemcpy(b->d_tw_half, th.data(), sizeof(float2) * (g.fft / 2), cudaMemcpyHostToDevice);
+    }
+  }
+  b->bl_L = 0;
+  b->d_bl_tw = b->d_bl_B = b->d_bl_chirp = nullptr;
+  if (ok && g.fft != 480 && !mixed_radix_window(g.window)) {
+    // chirp-z tables, in double: c[n] = e^{-i pi n^2 / N}, the filter e^{+i pi m^2 / N} for
+    // m = -(W-1) .. W laid out modulo L, its L-point transform divided by L
+    const int N = g.fft, W = g.window, L = chirp_length(N);
+    if (L > 0) {
+      std::vector<float2> tw(L), B(L), ch(W);
+      std::vector<double> br(L, 0.0), bi(L, 0.0);
+      for (int k = 0; k < L; k++) {
+        const double ph = -2.0 * M_PI * k / L;
+        tw[k] = make_float2((float)cos(ph), (float)sin(ph));
+      }
+      for (int n = 0; n < W; n++) {
+        const double ph = -M_PI * (double)(((long long)n * n) % (2LL * N)) / N;
+        ch[n] = make_float2((float)cos(ph), (float)sin(ph));
+      }
+      for (int m = -(W - 1); m <= W; m++) {
+        const double ph = M_PI * (double)(((long long)m * m) % (2LL * N)) / N;
+        const int at = ((m % L) + L) % L;
+        br[at] = cos(ph);
+        bi[at] = sin(ph);
+      }
+      std::vector<double> cr(L), ci(L);
+      for (int k = 0; k < L; k++) {
+        const double ph = -2.0 * M_PI * k / L;
+        cr[k] = cos(ph);
+        ci[k] = sin(ph);
+      }
+      for (int k = 0; k < L; k++) {
+        double sr = 0.0, si = 0.0;
+        for (int j = 0; j < L; j++) {
+          if (br[j] == 0.0 && bi[j] == 0.0) continue;
+          const int e = (int)(((long long)j * k) % L);
+          sr += br[j] * cr[e] - bi[j] * ci[e];
+          si += br[j] * ci[e] + bi[j] * cr[e];
+        }
+        B[k] = make_float2((float)(sr / L), (float)(si / L));
+      }
+      ok = dev_alloc(b, &b->d_bl_tw, L) && dev_alloc(b, &b->d_bl_B, L) && dev_alloc(b, &b->d_bl_chirp, W);
+      if (ok) {
+        cudaMemcpy(b->d_bl_tw, tw.data(), sizeof(float2) * L, cudaMemcpyHostToDevice);
+        cudaMemcpy(b->d_bl_B, B.data(), sizeof(float2) * L, cudaMemcpyHostToDevice);
+        cudaMemcpy(b->d_bl_chirp, ch.data(), sizeof(float2) * W, cudaMemcpyHostToDevice);
+        b->bl_L = L;
+      }
     }
   }
   // history, scratch, output
@@ -606,6 +696,10 @@ int launch_analysis(const WriteCall& w, long long done, long long prefix, cudaSt
   k1.tw_half = b->d_tw_half;
   k1.n_factors = b->n_factors;
   memcpy(k1.factors, b->factors, sizeof(k1.factors));
+  k1.bl_L = b->bl_L;
+  k1.bl_tw = b->d_bl_tw;
+  k1.bl_B = b->d_bl_B;
+  k1.bl_chirp = b->d_bl_chirp;
   k1.tap_spec = b->d_tap_spec;
   k1.tap_stride = b->max_new_frames;
   prof_mark(b, sa, 0, true);

@@ -511,6 +511,44 @@ __device__ __forceinline__ void butterfly_any(int R, const float2* x, float2* y,
   }
 }
 
+// nT transforms of length M (x[t * M + i]) as one autosort FFT, radices from the plan in
+// p; ping-pongs between x and y and returns the buffer that holds the result.  Ends
+// with a block barrier.
+template <int THREADS>
+__device__ __forceinline__ float2* stockham(float2* x, float2* y, int nT, int M, const K1Params& p,
+                                            const float2* s_twM, int tid) {
+  int st = 1;
+  for (int f = 0; f < p.n_factors; f++) {
+    const int R = p.factors[f];
+    const int m = p.plan_m[f];      // sub-transform length after this stage: n / R
+    const int per = p.plan_per[f];  // butterflies per transform = M / R = m * st
+    // floor(a / b) == int((a + 0.5) / b) in float for these small integers
+    const float rcp_per = __frcp_rn((float)per), rcp_st = __frcp_rn((float)st);
+    for (int b = tid; b < nT * per; b += THREADS) {
+      const int which = (int)(((float)b + 0.5f) * rcp_per);
+      const int idx = b - which * per;
+      const int pp = (int)(((float)idx + 0.5f) * rcp_st), q = idx - pp * st;
+      const float2* xi = x + which * M;
+      float2* yo = y + which * M;
+      switch (R) {
+        case 8: butterfly<8>(xi, yo, s_twM, M, m, st, pp, q); break;
+        case 5: butterfly<5>(xi, yo, s_twM, M, m, st, pp, q); break;
+        case 4: butterfly<4>(xi, yo, s_twM, M, m, st, pp, q); break;
+        case 3: butterfly<3>(xi, yo, s_twM, M, m, st, pp, q); break;
+        case 2: butterfly<2>(xi, yo, s_twM, M, m, st, pp, q); break;
+        case 7: butterfly_prime<7>(xi, yo, s_twM, M, m, st, pp, q); break;
+        case 11: butterfly_prime<11>(xi, yo, s_twM, M, m, st, pp, q); break;
+        case 13: butterfly_prime<13>(xi, yo, s_twM, M, m, st, pp, q); break;
+        default: butterfly_any(R, xi, yo, s_twM, M, m, st, pp, q); break;
+      }
+    }
+    __syncthreads();
+    float2* tmp = x; x = y; y = tmp;
+    st *= R;
+  }
+  return x;
+}
+
 }  // namespace
 
 template <int THREADS>
@@ -592,39 +630,7 @@ __global__ void __launch_bounds__(THREADS) k1_spectral_mixed(K1Params p) {
     __syncthreads();
 
     // ---- the four M-point FFTs ----------------------------------------------
-    float2* x = X;
-    float2* y = Y;
-    {
-      int st = 1;
-      for (int f = 0; f < p.n_factors; f++) {
-        const int R = p.factors[f];
-        const int m = p.plan_m[f];      // sub-transform length after this stage: n / R
-        const int per = p.plan_per[f];  // butterflies per transform = M / R = m * st
-        // floor(a / b) == int((a + 0.5) / b) in float for these small integers
-        const float rcp_per = __frcp_rn((float)per), rcp_st = __frcp_rn((float)st);
-        for (int b = tid; b < 4 * per; b += THREADS) {
-          const int which = (int)(((float)b + 0.5f) * rcp_per);
-          const int idx = b - which * per;
-          const int pp = (int)(((float)idx + 0.5f) * rcp_st), q = idx - pp * st;
-          const float2* xi = x + which * M;
-          float2* yo = y + which * M;
-          switch (R) {
-            case 8: butterfly<8>(xi, yo, s_twM, M, m, st, pp, q); break;
-            case 5: butterfly<5>(xi, yo, s_twM, M, m, st, pp, q); break;
-            case 4: butterfly<4>(xi, yo, s_twM, M, m, st, pp, q); break;
-            case 3: butterfly<3>(xi, yo, s_twM, M, m, st, pp, q); break;
-            case 2: butterfly<2>(xi, yo, s_twM, M, m, st, pp, q); break;
-            case 7: butterfly_prime<7>(xi, yo, s_twM, M, m, st, pp, q); break;
-            case 11: butterfly_prime<11>(xi, yo, s_twM, M, m, st, pp, q); break;
-            case 13: butterfly_prime<13>(xi, yo, s_twM, M, m, st, pp, q); break;
-            default: butterfly_any(R, xi, yo, s_twM, M, m, st, pp, q); break;
-          }
-        }
-        __syncthreads();
-        float2* tmp = x; x = y; y = tmp;
-        st *= R;
-      }
-    }
+    float2* x = stockham<THREADS>(X, Y, 4, M, p, s_twM, tid);
     // Z[t] of slot: x[(2 slot + (t & 1)) M + (t >> 1)]
 
     // ---- real-FFT split, power, energy (as in the 16 kHz kernel) -------------
@@ -744,6 +750,184 @@ __global__ void __launch_bounds__(THREADS) k1_spectral_mixed(K1Params p) {
             if (c > thr1 && l > thr1) acc1 += fabsf((c - l) + d21);
           }
         }
+      }
+    }
+    acc0 = warp_sum(acc0);
+    acc1 = warp_sum(acc1);
+    if (lane == 0) {
+      red[warp * 4 + 0] = acc0;
+      red[warp * 4 + 1] = acc1;
+    }
+    __syncthreads();
+    if (tid < 2) {
+      const int slot = tid;
+      const int k = kk + slot;
+      if (k >= k0 && k < k1) {
+        float t = 0.0f;
+        for (int w = 0; w < NWARP; w++) t += red[w * 4 + slot];
+        p.feat[(size_t)s * p.feat_stride + (k - kA)] = make_float2(e_slot[slot], t * 0.34657359027997264f);  // ln2 / 2
+      }
+    }
+    linv_prev = linv_slot[1];
+    int t = ip; ip = ib; ib = ia; ia = t;  // slot B becomes "previous"
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Chirp-z (Bluestein) path: windows the mixed-radix kernel cannot factor, e.g.
+// 44.1 kHz where W = 661 is prime.  With c[n] = e^{-i pi n^2 / N},
+//   X[k] = c[k] sum_n (v[n] c[n]) conj(c)[k - n],
+// a convolution carried out with two L-point FFTs (L >= N, 7-smooth) per window
+// on the same Stockham machinery; only |X[k]| is needed, so the final chirp
+// multiplication and both conjugations of the inverse transform drop out.
+// ---------------------------------------------------------------------------
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k1_spectral_bluestein(K1Params p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const Geometry& g = p.g;
+  const int W = g.window, S = g.step, P = g.partial, N = g.fft, L = p.bl_L, H = N / 2;
+  const int HP = (H + 3) & ~3;  // row pitch of lmag
+  constexpr int NWARP = THREADS / 32;
+  float2* X = reinterpret_cast<float2*>(smem_raw);  // [2][L]
+  float2* Y = X + 2 * L;                             // [2][L]
+  float2* s_tw = Y + 2 * L;                          // [L]  W_L^k
+  float2* s_B = s_tw + L;                            // [L]  FFT of the chirp filter / L
+  float2* s_ch = s_B + L;                            // [W]  chirp
+  float* s_win = reinterpret_cast<float*>(s_ch + W + (W & 1));  // [W]  Hamming / 32768
+  float* lmag = s_win + ((W + 3) & ~3);              // [3][HP]
+  float* red = lmag + 3 * HP;                        // [NWARP][4]
+  short* samp = reinterpret_cast<short*>(red + NWARP * 4);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < L; i += THREADS) {
+    s_tw[i] = p.bl_tw[i];
+    s_B[i] = p.bl_B[i];
+  }
+  for (int i = tid; i < W; i += THREADS) {
+    s_ch[i] = p.bl_chirp[i];
+    s_win[i] = p.window[i] * 3.0517578125e-05f;
+  }
+
+  const long long item = blockIdx.x;
+  const int s = (int)(item / p.runs_per_stream);
+  const int run = (int)(item % p.runs_per_stream);
+  if (s >= p.n_streams) return;
+  const Range rg = write_range(p.st.total, p.counts, p.frames, p.done, s);
+  const long long t_old = rg.t_old, t_new = rg.t_new;
+  const int kA = frames_analyzed(g, t_old);      // scratch rows count from here
+  const int kD = frames_analyzed(g, rg.t_done);  // first window of this launch
+  const int kB = frames_analyzed(g, t_new);
+  const int k0 = kD + run * kRun;
+  if (k0 >= kB) return;
+  const int k1 = min(k0 + kRun, kB);
+
+  Source src;
+  src.channels = g.channels;
+  src.hist = p.hist + (size_t)s * p.hist_stride;
+  src.in = p.in ? p.in + (size_t)s * p.in_stride_frames * g.channels : nullptr;
+  src.hist_base = p.st.hist_base[s];
+  src.t_old = t_old;
+  src.t_new = t_new;
+
+  const long long base = (long long)(k0 - 1) * S;
+  const int need = (k1 - k0 + 1) * S + P;
+  stage_mono<THREADS, short>(src, base, need, t_new, samp, nullptr, tid);
+  __syncthreads();
+
+  int ip = 0, ia = 1, ib = 2;  // rotating rows of lmag: previous window, slot A, slot B
+  float linv_prev = 0.0f;
+
+  for (int kk = k0 - 1; kk < k1; kk += 2) {
+    // ---- pass 0: int16 -> float, pre-emphasis, Hamming, chirp ---------------
+    for (int i = tid; i < 2 * L; i += THREADS) {
+      const int slot = i >= L ? 1 : 0;
+      const int n = i - slot * L;
+      const int k = kk + slot;
+      float2 a = make_float2(0.0f, 0.0f);
+      if (n < W && k >= 0 && k < k1) {
+        const int o = (k - (k0 - 1)) * S;
+        const float xm = (float)((n > 0) ? samp[o + n - 1] : (k >= 1 ? samp[o + P - 1] : 0));
+        const float x0 = (float)samp[o + n];
+        const float v = __fmul_rn(__fmaf_rn(-kPreLo, xm, __fmaf_rn(-kPreHi, xm, x0)), s_win[n]);
+        a = cscale(s_ch[n], v);
+      }
+      X[i] = a;
+    }
+    __syncthreads();
+
+    // ---- convolution with the chirp filter: FFT, multiply, FFT again --------
+    float2* x = stockham<THREADS>(X, Y, 2, L, p, s_tw, tid);
+    for (int i = tid; i < 2 * L; i += THREADS) {
+      const int j = i >= L ? i - L : i;
+      const float2 t = cmul(x[i], s_B[j]);
+      x[i] = make_float2(t.x, -t.y);  // conj: the second forward transform then inverts
+    }
+    __syncthreads();
+    x = stockham<THREADS>(x, x == X ? Y : X, 2, L, p, s_tw, tid);
+    // |X[k]| of slot = |x[slot * L + k]|, k = 0 .. H
+
+    // ---- power, energy -------------------------------------------------------
+    float e0 = 0.0f, e1 = 0.0f, mx0 = 0.0f, mx1 = 0.0f;
+    for (int i = tid; i < 2 * (H + 1); i += THREADS) {
+      const int slot = i >= H + 1 ? 1 : 0;
+      const int t = i - slot * (H + 1);
+      const int k = kk + slot;
+      const float2 z = x[slot * L + t];
+      const float pw = __fadd_rn(__fmul_rn(z.x, z.x), __fmul_rn(z.y, z.y));
+      if (t < H) {
+        lmag[(slot == 0 ? ia : ib) * HP + t] = __log2f(pw);
+        if (t >= 1) {
+          if (slot == 0) { e0 += pw; mx0 = fmaxf(mx0, pw); }
+          else { e1 += pw; mx1 = fmaxf(mx1, pw); }
+        }
+      }
+      if (p.tap_spec && k >= k0 && k < k1) {
+        float* tap = p.tap_spec + ((size_t)s * p.tap_stride + (k - kA)) * N;
+        const float m = __fsqrt_rn(pw);
+        tap[t] = m;
+        if (t >= 1 && t < H) tap[N - t] = m;
+      }
+    }
+    e0 = warp_sum(e0);
+    e1 = warp_sum(e1);
+    mx0 = warp_max(mx0);
+    mx1 = warp_max(mx1);
+    if (lane == 0) {
+      red[warp * 4 + 0] = e0;
+      red[warp * 4 + 1] = e1;
+      red[warp * 4 + 2] = mx0;
+      red[warp * 4 + 3] = mx1;
+    }
+    __syncthreads();
+    float e_slot[2] = {0.0f, 0.0f}, pmax_slot[2] = {0.0f, 0.0f};
+#pragma unroll
+    for (int w = 0; w < NWARP; w++) {
+      e_slot[0] += red[w * 4 + 0];
+      e_slot[1] += red[w * 4 + 1];
+      pmax_slot[0] = fmaxf(pmax_slot[0], red[w * 4 + 2]);
+      pmax_slot[1] = fmaxf(pmax_slot[1], red[w * 4 + 3]);
+    }
+    __syncthreads();  // red is reused below
+
+    // ---- spectral difference against the previous window (log2 domain) -------
+    float linv_slot[2];
+    linv_slot[0] = -__log2f(__fsqrt_rn(e_slot[0]) + 2.2204e-16f);
+    linv_slot[1] = -__log2f(__fsqrt_rn(e_slot[1]) + 2.2204e-16f);
+    const float thr0 = __log2f(pmax_slot[0]) - 13.287712379549449f;  // log2(1e4)
+    const float thr1 = __log2f(pmax_slot[1]) - 13.287712379549449f;
+    const float d20 = 2.0f * (linv_slot[0] - linv_prev);
+    const float d21 = 2.0f * (linv_slot[1] - linv_slot[0]);
+    float acc0 = 0.0f, acc1 = 0.0f;
+    for (int i = tid; i < 2 * (H - 1); i += THREADS) {
+      const int slot = i >= H - 1 ? 1 : 0;
+      const int bin = 1 + i - slot * (H - 1);
+      const float c = lmag[(slot == 0 ? ia : ib) * HP + bin];
+      const float l = lmag[(slot == 0 ? ip : ia) * HP + bin];
+      if (slot == 0) {
+        if (c > thr0 && l > thr0) acc0 += fabsf((c - l) + d20);
+      } else {
+        if (c > thr1 && l > thr1) acc1 += fabsf((c - l) + d21);
       }
     }
     acc0 = warp_sum(acc0);
@@ -952,7 +1136,39 @@ cudaError_t launch_k1(const K1Params& p, cudaStream_t stream) {
       }
       mixed = rest == 1;
     }
-    if (mixed) {
+    if (!mixed && p.bl_L > 0 && !getenv("SPEEDY_K1_GENERIC")) {
+      // chirp-z: the plan is for the L-point transforms
+      const int L = p.bl_L;
+      const int pref[] = {8, 4, 5, 3, 2, 7};
+      np = 0;
+      rest = L;
+      for (int r : pref) {
+        while (rest % r == 0 && np < kMaxFactors) {
+          plan[np++] = r;
+          rest /= r;
+        }
+      }
+      if (rest != 1) return cudaErrorInvalidValue;
+      q.n_factors = np;
+      for (int i = 0, n = L; i < np; i++) {
+        q.factors[i] = plan[i];
+        n /= plan[i];
+        q.plan_m[i] = n;
+        q.plan_per[i] = L / plan[i];
+      }
+      const int HP = (N / 2 + 3) & ~3;
+      const size_t smem = (size_t)(6 * L + W + (W & 1)) * sizeof(float2) + (size_t)(((W + 3) & ~3) + 3 * HP) * sizeof(float) +
+                          (THREADS / 32) * 4 * sizeof(float) +
+                          (size_t)((kRun + 1) * p.g.step + p.g.partial + 16) * sizeof(short);
+      static int attr_smem_b = 0;
+      if ((int)smem > attr_smem_b) {
+        cudaError_t e = cudaFuncSetAttribute(k1_spectral_bluestein<THREADS>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_smem_b = (int)smem;
+      }
+      k1_spectral_bluestein<THREADS><<<(unsigned)items, THREADS, smem, stream>>>(q);
+    } else if (mixed) {
       q.n_factors = np;
       for (int i = 0, n = M; i < np; i++) {
         q.factors[i] = plan[i];

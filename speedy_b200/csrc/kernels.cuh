@@ -46,6 +46,11 @@ struct K1Params {
   int factors[kMaxFactors];      // generic path: radices of N; mixed path: radices of M = W/2
   int plan_m[kMaxFactors];       // mixed path: sub-transform length after each stage
   int plan_per[kMaxFactors];     // mixed path: butterflies per transform in each stage
+  // chirp-z (Bluestein) path for windows the mixed-radix kernel cannot factor (44.1 kHz: W = 661):
+  int bl_L;                      // convolution length (0: not used); the plan above is then for L
+  const float2* bl_tw;           // [L] W_L^k
+  const float2* bl_B;            // [L] FFT_L of the chirp filter e^{+i pi m^2 / N}, divided by L
+  const float2* bl_chirp;        // [W] e^{-i pi n^2 / N}
   // optional tap: [n][tap_stride][N]
   float* tap_spec;
   int tap_stride;
