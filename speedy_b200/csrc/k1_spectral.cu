@@ -24,8 +24,11 @@
 // flight per warp so that both butterfly passes fill the warp: 2 x 30 radix-8
 // butterflies, then 32 radix-15 butterflies.
 //
-// Any other rate (N = 660, 720, 1440, ...) goes through the generic kernel: one
-// CTA per run, a mixed-radix Stockham FFT in shared memory.
+// Any other rate: k1_spectral_mixed (even windows whose half factors into radices up
+// to 13: N = 660, 720, 960, 1440 ...: the same packed decomposition, the transforms
+// as a Stockham FFT in shared memory, one CTA per run), k1_spectral_bluestein (odd or
+// prime windows, 44.1 kHz: chirp-z on the same machinery); k1_spectral_generic is the
+// O(N R) fallback they replaced.
 #include <stdlib.h>
 
 #include "kernels.cuh"
