@@ -211,6 +211,19 @@ __global__ void __launch_bounds__(WARPS * 32) k1_spectral_480(K1Params p) {
   // pass 2: lane = slot*16 + q*8 + j1 handles one radix-15 butterfly
   const int slot2 = lane >> 4, q2 = (lane >> 3) & 1, j1_2 = lane & 7;
 
+  // real-FFT split: bins t = 1 + lane + 32 j, j < 4; in the last step lane 23 lands on
+  // t = 120, lane 24 takes t = 0, lanes 25-31 idle
+  int split_t[4];
+  float2 split_w[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    int t = 1 + lane + 32 * j;
+    if (t == 121) t = 0;
+    else if (t > 121) t = -1;
+    split_t[j] = t;
+    split_w[j] = s_tw480[t < 0 ? 0 : t];
+  }
+
   int ip = 0, ia = 1, ib = 2;  // rotating indices into ws.mag
   float linv_prev = 0.0f;
 
@@ -320,50 +333,41 @@ __global__ void __launch_bounds__(WARPS * 32) k1_spectral_480(K1Params p) {
       // Real-FFT split, two bins per step.  With S = (Z[t] + conj Z[240-t]) / 2,
       // D = (Z[t] - conj Z[240-t]) / 2 and P = W_480^t D:
       //   X[t] = S - i P,   X[240-t] = conj(S) - i conj(P)      (W_480^(240-t) = -conj W_480^t)
-      for (int t = 1 + lane; t < 120; t += 32) {
-        const float2 zk = Z[t], zm = Z[240 - t];
-        const float sx = 0.5f * (zk.x + zm.x), sy = 0.5f * (zk.y - zm.y);
-        const float dx = 0.5f * (zk.x - zm.x), dy = 0.5f * (zk.y + zm.y);
-        const float2 w = s_tw480[t];
+      // The halves are left out: everything below is 2 X, its square 4 |X|^2 (exact
+      // scalings), which only shifts every log2 by the same 2 and is undone once for the
+      // energy.  t = 120 pairs with itself and t = 0 with Z[240] = Z[0] (its partner is
+      // bin N/2, kept for the tap only): lanes 23 and 24 of the last step take them.
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int t = split_t[j];
+        if (t < 0) continue;
+        const int u = t == 0 ? 0 : 240 - t;
+        const float2 zk = Z[t], zm = Z[u];
+        const float sx = zk.x + zm.x, sy = zk.y - zm.y;
+        const float dx = zk.x - zm.x, dy = zk.y + zm.y;
+        const float2 w = split_w[j];
         const float px = w.x * dx - w.y * dy, py = w.x * dy + w.y * dx;
-        const float re0 = sx + py, im0 = sy - px;    // X[t]
-        const float re1 = sx - py, im1 = sy + px;    // X[240-t] up to the sign of im
+        const float re0 = sx + py, im0 = sy - px;    // 2 X[t]
+        const float re1 = sx - py, im1 = sy + px;    // 2 X[240-t] up to the sign of im
         // speedy.c:434-436 squares and sums in float; so does this
-        const float p0 = __fadd_rn(__fmul_rn(re0, re0), __fmul_rn(im0, im0));
-        const float p1 = __fadd_rn(__fmul_rn(re1, re1), __fmul_rn(im1, im1));
-        lmag[t] = __log2f(p0);
-        lmag[240 - t] = __log2f(p1);
-        e += p0 + p1;
-        mx = fmaxf(mx, fmaxf(p0, p1));
+        const float q0 = __fadd_rn(__fmul_rn(re0, re0), __fmul_rn(im0, im0));
+        const float q1 = __fadd_rn(__fmul_rn(re1, re1), __fmul_rn(im1, im1));
+        lmag[t] = __log2f(q0);
+        if (t != 0) lmag[240 - t] = __log2f(q1);
+        const float c0 = t >= 1 ? q0 : 0.0f;               // bin 0 is not part of the energy
+        const float c1 = (t >= 1 && t < 120) ? q1 : 0.0f;  // bin N/2 neither; bin 120 counts once
+        e += c0 + c1;
+        mx = fmaxf(mx, fmaxf(c0, c1));
         if (tap) {
-          const float m0 = __fsqrt_rn(p0), m1 = __fsqrt_rn(p1);
+          const float m0 = 0.5f * __fsqrt_rn(q0), m1 = 0.5f * __fsqrt_rn(q1);
           tap[t] = m0;
-          tap[480 - t] = m0;
+          if (t != 0) tap[480 - t] = m0;
           tap[240 - t] = m1;
           tap[240 + t] = m1;
         }
       }
-      if (lane == 0) {
-        // bins 0, N/4 and N/2: X[0] = Re Z0 + Im Z0, X[N/2] = Re Z0 - Im Z0,
-        // X[120] = conj(Z[120]) (W_480^120 = -i)
-        const float2 z0 = Z[0], zq = Z[120];
-        const float x0 = z0.x + z0.y;
-        const float p0 = __fmul_rn(x0, x0);
-        const float pq = __fadd_rn(__fmul_rn(zq.x, zq.x), __fmul_rn(zq.y, zq.y));
-        lmag[0] = __log2f(p0);
-        lmag[120] = __log2f(pq);
-        e += pq;
-        mx = fmaxf(mx, pq);
-        if (tap) {
-          tap[0] = fabsf(x0);
-          tap[240] = fabsf(z0.x - z0.y);
-          const float mq = __fsqrt_rn(pq);
-          tap[120] = mq;
-          tap[360] = mq;
-        }
-      }
-      e_slot[slot] = warp_sum(e);
-      pmax_slot[slot] = warp_max(mx);
+      e_slot[slot] = 0.25f * warp_sum(e);
+      pmax_slot[slot] = warp_max(mx);  // 4 max |X|^2: the same shift as the stored log2 values
     }
     __syncwarp();
 
