@@ -45,6 +45,23 @@ static void set_error(const std::string& e) { g_error = e; }
 // delayed audio Sonic has not consumed yet plus the analysis overlap), advance
 // the stream total.  soniclib.c keeps the same data in its ring of 10 ms buffers
 // (soniclib.c:186-233) and upstream Sonic in its input FIFO.
+// count int16 elements, 16 bytes at a time where source and destination are equally aligned
+__device__ __forceinline__ void copy_shorts(int16_t* d, const int16_t* src, long long total, int tid, int nthreads) {
+  const size_t ms = reinterpret_cast<size_t>(src) & 15, md = reinterpret_cast<size_t>(d) & 15;
+  if (ms == md) {
+    long long head = ms ? (long long)((16 - ms) >> 1) : 0;
+    if (head > total) head = total;
+    const long long nv = (total - head) / 8;
+    for (long long i = tid; i < head; i += nthreads) d[i] = src[i];
+    const int4* sv = reinterpret_cast<const int4*>(src + head);
+    int4* dv = reinterpret_cast<int4*>(d + head);
+    for (long long i = tid; i < nv; i += nthreads) dv[i] = sv[i];
+    for (long long i = head + nv * 8 + tid; i < total; i += nthreads) d[i] = src[i];
+  } else {
+    for (long long i = tid; i < total; i += nthreads) d[i] = src[i];
+  }
+}
+
 __global__ void __launch_bounds__(128) tail_kernel(TailParams p) {
   const int s = blockIdx.x;
   const Geometry& g = p.g;
@@ -61,12 +78,12 @@ __global__ void __launch_bounds__(128) tail_kernel(TailParams p) {
   src.t_old = t_old;
   src.t_new = t_new;
   int16_t* dst = p.hist_dst + (size_t)s * p.hist_stride;
-  const long long total = (t_new - nb) * g.channels;
-  const long long first = nb * g.channels;
-  for (long long i = threadIdx.x; i < total; i += blockDim.x) {
-    long long e = first + i;
-    long long frame = e / g.channels;
-    dst[i] = (int16_t)src.raw(frame, (int)(e - frame * g.channels));
+  // two contiguous pieces: what stays of the old tail, then the end of this write
+  const int C = g.channels;
+  const long long f0 = nb > t_old ? nb : t_old;  // first frame taken from the caller's buffer
+  if (nb < t_old) copy_shorts(dst, src.hist + (nb - old_base) * C, (t_old - nb) * C, threadIdx.x, blockDim.x);
+  if (t_new > f0) {
+    copy_shorts(dst + (f0 - nb) * C, src.in + (f0 - t_old) * C, (t_new - f0) * C, threadIdx.x, blockDim.x);
   }
   __syncthreads();  // all reads of total/hist_base above are done
   if (threadIdx.x == 0) {
