@@ -61,31 +61,39 @@ struct Source {
   }
 };
 
-// Stage `count` mono samples (channel average, soniclib.c:271-274) of frames
-// [start, start + count) into shared memory, dst[i] = frame start + i.  Frames
-// outside [src.hist_base, lim) read as 0.  The bulk comes from the caller's buffer
-// with 16-byte loads (8 int16 per load, several in flight per thread); only the
-// pieces in the carried history, or a misaligned head/tail, go one sample at a
-// time.  raw16 (optional, channels > 1) receives the interleaved samples too.
+// One mono value (channel average with C integer division, soniclib.c:271-274) of an
+// interleaved frame; raw16 (optional) receives the frame's samples too.
+template <typename T>
+__device__ __forceinline__ void stage_frame(const int16_t* p, int C, T* dst, short* raw16) {
+  if (C == 1) {
+    *dst = (T)p[0];
+  } else {
+    int sum = 0;
+    for (int c = 0; c < C; c++) {
+      const int x = p[c];
+      sum += x;
+      if (raw16) raw16[c] = (short)x;
+    }
+    *dst = (T)(sum / C);
+  }
+}
+
+// Frames [a, b) of one contiguous source (ptr[0] is the first sample of frame f0) into
+// dst[f - start]: 16-byte loads (8 int16, four in flight per thread) over the part
+// that is 16-byte aligned in the source, one frame at a time at its ragged ends.
 template <int THREADS, typename T>
-__device__ __forceinline__ void stage_mono(const Source& src, long long start, int count, long long lim,
-                                           T* dst, short* raw16, int tid) {
-  const int C = src.channels;
-  if (lim > src.t_new) lim = src.t_new;
-  // frames served by the vector path: [v0, v1), inside the caller's buffer
-  long long v0 = start > src.t_old ? start : src.t_old;
-  long long v1 = start + count < lim ? start + count : lim;
-  const bool vec_ok = src.in != nullptr && (C == 1 || C == 2) && v1 - v0 >= 64 &&
-                      ((reinterpret_cast<size_t>(src.in) & (C == 2 ? 3 : 1)) == 0);
-  if (vec_ok) {
-    // align v0 up / v1 down to 16-byte boundaries of the caller's buffer
+__device__ __forceinline__ void stage_span(const int16_t* ptr, long long f0, int C, long long a, long long b,
+                                           long long start, T* dst, short* raw16, int tid) {
+  if (b <= a) return;
+  long long v0 = a, v1 = a;  // frames served by the vector path: [v0, v1)
+  if ((C == 1 || C == 2) && b - a >= 64 && ((reinterpret_cast<size_t>(ptr) & (C == 2 ? 3 : 1)) == 0)) {
     const int fpv = 8 / C;  // frames per 16-byte vector
-    const long long a0 = (long long)((reinterpret_cast<size_t>(src.in) >> 1) & 7) / C;  // frame offset of base
-    const long long g0 = v0 - src.t_old + a0, g1 = v1 - src.t_old + a0;
+    const long long a0 = (long long)((reinterpret_cast<size_t>(ptr) >> 1) & 7) / C;  // frame offset of ptr in its vector
+    const long long g0 = a - f0 + a0, g1 = b - f0 + a0;
     const long long c0 = (g0 + fpv - 1) / fpv, c1 = g1 / fpv;
     if (c1 > c0) {
-      const long long fv0 = src.t_old + c0 * fpv - a0;  // first frame of vector c0
-      const int4* vp = reinterpret_cast<const int4*>(src.in + (fv0 - src.t_old) * C);
+      const long long fv0 = f0 + c0 * fpv - a0;  // first frame of vector c0
+      const int4* vp = reinterpret_cast<const int4*>(ptr + (fv0 - f0) * C);
       const int nvec = (int)(c1 - c0);
       T* d = dst + (fv0 - start);
       short* r = raw16 ? raw16 + (fv0 - start) * C : nullptr;
@@ -122,34 +130,47 @@ __device__ __forceinline__ void stage_mono(const Source& src, long long start, i
       }
       v0 = fv0;
       v1 = fv0 + (long long)nvec * fpv;
-    } else {
-      v1 = v0;
     }
-  } else {
-    v1 = v0;
   }
-  // everything else: [start, v0) and [v1, start + count)
-  const long long end = start + count;
-  const int n_head = (int)(v0 - start), n_tail = (int)(end - v1);
+  // the ragged ends (or everything): [a, v0) and [v1, b)
+  const int n_head = (int)(v0 - a), n_tail = (int)(b - v1);
   for (int i = tid; i < n_head + n_tail; i += THREADS) {
-    const long long f = i < n_head ? start + i : v1 + (i - n_head);
-    int m = 0;
-    if (f >= src.hist_base && f < lim) {
-      if (C == 1) {
-        m = src.raw(f, 0);
-      } else {
-        int sum = 0;
-        for (int c = 0; c < C; c++) {
-          const int x = src.raw(f, c);
-          sum += x;
-          if (raw16) raw16[(f - start) * C + c] = (short)x;
-        }
-        m = sum / C;
-      }
-    } else if (raw16 && C > 1) {
+    const long long f = i < n_head ? a + i : v1 + (i - n_head);
+    stage_frame<T>(ptr + (f - f0) * C, C, dst + (f - start), raw16 ? raw16 + (f - start) * C : nullptr);
+  }
+}
+
+// Stage `count` mono samples (channel average, soniclib.c:271-274) of frames
+// [start, start + count) into shared memory, dst[i] = frame start + i.  Frames
+// outside [src.hist_base, lim) read as 0.  The carried history and the caller's
+// buffer are each one contiguous span.  raw16 (optional, channels > 1) receives the
+// interleaved samples too.
+template <int THREADS, typename T>
+__device__ __forceinline__ void stage_mono(const Source& src, long long start, int count, long long lim,
+                                           T* dst, short* raw16, int tid) {
+  const int C = src.channels;
+  if (lim > src.t_new) lim = src.t_new;
+  const long long end = start + count;
+  // [h0, h1) from the history, [i0, i1) from the caller's buffer, zeros elsewhere
+  long long h0 = start > src.hist_base ? start : src.hist_base;
+  long long h1 = end < src.t_old ? end : src.t_old;
+  if (h1 > lim) h1 = lim;
+  if (h1 < h0) h1 = h0;
+  long long i0 = start > src.t_old ? start : src.t_old;
+  long long i1 = end < lim ? end : lim;
+  if (i1 < i0) i1 = i0;
+  stage_span<THREADS, T>(src.hist, src.hist_base, C, h0, h1, start, dst, raw16, tid);
+  if (src.in) stage_span<THREADS, T>(src.in, src.t_old, C, i0, i1, start, dst, raw16, tid);
+  // zeros: before the history begins, and from the end of the data on
+  const long long z0 = h0 < end ? h0 : end;                        // [start, z0)
+  const long long z1 = (src.in && i1 > i0) ? i1 : (h1 > start ? h1 : start);  // [z1, end)
+  const int nz0 = (int)(z0 - start), nz1 = (int)(end - (z1 < end ? z1 : end));
+  for (int i = tid; i < nz0 + nz1; i += THREADS) {
+    const long long f = i < nz0 ? start + i : z1 + (i - nz0);
+    dst[f - start] = (T)0;
+    if (raw16 && C > 1) {
       for (int c = 0; c < C; c++) raw16[(f - start) * C + c] = 0;
     }
-    dst[f - start] = (T)m;
   }
 }
 
