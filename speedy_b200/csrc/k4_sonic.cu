@@ -610,7 +610,7 @@ __host__ __device__ inline size_t k4_stream_smem(const Geometry& g, int buf_fram
 // MINB: resident CTAs per SM the register allocation is held to (1 = unconstrained).
 // Few streams: registers are free, latency is what counts.  Many streams: 16 resident
 // warps per SM hide the chain's latency, worth a tighter allocation.
-template <int NW, int MINB, int CH>
+template <int NW, int MINB, int CH, bool HOSTMAP>
 __global__ void __launch_bounds__(NW * 32, MINB) k4_sonic(K4Params p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int s = blockIdx.x;
@@ -644,7 +644,23 @@ __global__ void __launch_bounds__(NW * 32, MINB) k4_sonic(K4Params p) {
   k.bufStart = 0;
   k.bufLen = 0;
   k.dec_magic = (unsigned)((0x100000000ULL + (unsigned)(g.channels * k.skip) - 1) / (unsigned)(g.channels * k.skip));
-  {
+  if (HOSTMAP) {
+    // short launches (10 ms streaming writes, flush): the lane mappings come from the
+    // launcher (k4_lane_map), the kernel's own set-up would be half of its instructions
+    const unsigned m = p.lane_map[threadIdx.x];
+    k.cGi = (int)(m & 0xffu) - 1;
+    k.cSub = (int)((m >> 8) & 0xffu);
+    k.cG = (int)((m >> 16) & 0xffu);
+    k.cMaxG = p.c_max_g;
+    k.fG = p.f_g;
+    k.fPerRound = p.f_per_round;
+    __builtin_assume(k.cG >= 1 && k.cG <= 32 && k.cSub >= 0 && k.cSub < 32 && k.cMaxG >= 1 && k.cMaxG <= 32);
+    __builtin_assume(k.fG >= 1 && k.fG <= 32 && k.fPerRound >= 1);
+    const int gpw = 32 / k.fG;  // groups per warp
+    const int slot = k.lane / k.fG;
+    k.fg = k.lane - slot * k.fG;
+    k.fGi0 = slot < gpw ? k.warp * gpw + slot : (1 << 30);  // idle lanes never match
+  } else {
     // lane mappings (lags rounded out to groups of four)
     const int c_lo = k.minP / k.skip, c_hi = k.maxP / k.skip;
     const int qlo = c_lo >> 2, qhi = c_hi >> 2;
@@ -811,6 +827,60 @@ __global__ void __launch_bounds__(NW * 32, MINB) k4_sonic(K4Params p) {
   }
 }
 
+// Lane assignment of the two AMDF searches for NW warps per stream (lags rounded out to
+// groups of four).
+//   coarse: group q has q + 1 blocks.  Groups are dealt to the warps largest first
+//   (least-loaded warp takes the next one); inside a warp every group gets
+//   ceil((q + 1) / T) adjacent lanes with the smallest T that fits 32 lanes.
+//   fine (and single-stage) pass: fG adjacent lanes per group, groups never straddle a
+//   warp: the largest fG with NW * (32 / fG) >= the group count.
+static void k4_lane_map(K4Params& p, int NW) {
+  const Geometry& g = p.g;
+  const int c_lo = g.min_period / g.skip, c_hi = g.max_period / g.skip;
+  const int qlo = c_lo >> 2, qhi = c_hi >> 2;
+  int load[4] = {0, 0, 0, 0};
+  int owner[kMaxGroups];
+  for (int q = qhi; q >= qlo; q--) {
+    int best_w = 0;
+    for (int w = 1; w < NW; w++) {
+      if (load[w] < load[best_w]) best_w = w;
+    }
+    owner[q - qlo] = best_w;
+    load[best_w] += q + 1;
+  }
+  p.c_max_g = 1;
+  for (int i = 0; i < 128; i++) p.lane_map[i] = 1u << 16;  // idle: no group, cG = 1
+  for (int w = 0; w < NW; w++) {
+    int T = 1;
+    for (;; T++) {
+      int sum = 0;
+      for (int q = qlo; q <= qhi; q++) {
+        if (owner[q - qlo] == w) sum += (q + T) / T;
+      }
+      if (sum <= 32) break;
+    }
+    int first = 0;
+    for (int q = qlo; q <= qhi; q++) {
+      if (owner[q - qlo] != w) continue;
+      const int n = (q + T) / T;
+      for (int l = first; l < first + n; l++) {
+        p.lane_map[w * 32 + l] = (unsigned)(q - qlo + 1) | ((unsigned)(l - first) << 8) | ((unsigned)n << 16);
+      }
+      first += n;
+    }
+  }
+  // cMaxG is per warp in the kernel's combine(); the largest over the warps is a valid bound
+  for (int i = 0; i < 32 * NW; i++) {
+    const int n = (int)((p.lane_map[i] >> 16) & 0xffu);
+    if (n > p.c_max_g) p.c_max_g = n;
+  }
+  const int fine_groups = g.skip != 1 ? 2 * g.skip + 2 : qhi - qlo + 1;
+  int fG = 32;
+  while (fG > 1 && NW * (32 / fG) < fine_groups) fG--;
+  p.f_g = fG;
+  p.f_per_round = NW * (32 / fG);
+}
+
 static int k4_buf_frames(const Geometry& g, int n_streams) {
   // window: several search spans; smaller when many streams share an SM
   int n = (n_streams >= 148 * 12 ? 4 : 8) * g.max_required;
@@ -831,24 +901,30 @@ static int k4_buf_frames(const Geometry& g, int n_streams) {
   return n & ~63;
 }
 
-template <int NW, int MINB, int CH>
+template <int NW, int MINB, int CH, bool HOSTMAP>
 static cudaError_t launch_k4_c(K4Params& p, cudaStream_t stream) {
   const size_t smem = k4_stream_smem(p.g, p.buf_frames);
   static size_t attr = 0;
   if (smem > attr) {
-    cudaError_t e =
-        cudaFuncSetAttribute(k4_sonic<NW, MINB, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k4_sonic<NW, MINB, CH, HOSTMAP>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     attr = smem;
   }
-  k4_sonic<NW, MINB, CH><<<p.n_streams, NW * 32, smem, stream>>>(p);
+  k4_sonic<NW, MINB, CH, HOSTMAP><<<p.n_streams, NW * 32, smem, stream>>>(p);
   count_launch();
   return cudaGetLastError();
 }
 
 template <int NW, int MINB>
 static cudaError_t launch_k4_t(K4Params& p, cudaStream_t stream) {
-  return p.g.channels == 1 ? launch_k4_c<NW, MINB, 1>(p, stream) : launch_k4_c<NW, MINB, 0>(p, stream);
+  // short launches take the variant with host-computed lane mappings
+  const bool short_launch = p.flush || p.frames - p.done <= p.g.rate;
+  if (short_launch) {
+    k4_lane_map(p, NW);
+    return p.g.channels == 1 ? launch_k4_c<NW, MINB, 1, true>(p, stream) : launch_k4_c<NW, MINB, 0, true>(p, stream);
+  }
+  return p.g.channels == 1 ? launch_k4_c<NW, MINB, 1, false>(p, stream) : launch_k4_c<NW, MINB, 0, false>(p, stream);
 }
 
 cudaError_t launch_k4(const K4Params& p0, cudaStream_t stream) {

@@ -99,6 +99,10 @@ struct K4Params {
   long long out_capacity;        // sample frames per stream
   int threads_per_stream;
   int buf_frames;                // shared-memory window, filled by the launcher
+  // lane assignment of the AMDF searches, filled by the launcher (k4_sonic.cu):
+  // per lane cGi + 1 (0 = idle) | cSub << 8 | cG << 16, then the per-kernel scalars
+  unsigned lane_map[128];
+  int c_max_g, f_g, f_per_round;
 };
 cudaError_t launch_k4(const K4Params& p, cudaStream_t stream);
 
