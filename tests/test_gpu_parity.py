@@ -364,3 +364,31 @@ def test_process_host_api_matches_device_path():
             assert np.array_equal(got[s, :cnt_b[s]], out_b[s, :cnt_b[s]]), s
             assert not got[s, cnt_b[s]:].any()
     b.close()
+
+
+def test_process_tapered_chunks_match_device_path():
+    """Long enough (12 s) for speedyBatchProcess to taper its last chunks: same bytes as
+    one write + flush + read, ragged stream lengths included."""
+    n, rate, frames = 6, 16000, 16000 * 12
+    pcm = ol.synth(77, n, rate, 1, frames)
+    cap = frames + 4096
+    b = sb.Batch(n, rate, 1, speed=1.8, nonlinear=1.0, feedback=0.1, max_write_frames=frames, out_capacity=cap)
+    b.write(pcm)
+    b.flush()
+    out_b, cnt_b = b.read(cap)
+    b.reset()
+    out_a, cnt_a = b.process(pcm, cap)  # pageable buffers: rectangular copy-out path
+    assert np.array_equal(cnt_a, cnt_b)
+    for s in range(n):
+        assert np.array_equal(out_a[s, :cnt_a[s]], out_b[s, :cnt_b[s]]), s
+    h_in = torch.from_numpy(pcm).pin_memory()
+    h_out = torch.zeros((n, cap, 1), dtype=torch.int16).pin_memory()
+    h_cnt = torch.zeros(n, dtype=torch.int32)
+    b.process_ptr(h_in, frames, h_out, cap, h_cnt)  # pinned: device-side scatter into host memory
+    b.close()
+    assert np.array_equal(h_cnt.numpy(), cnt_b)
+    got = h_out.numpy()
+    for s in range(n):
+        assert np.array_equal(got[s, :cnt_b[s]], out_b[s, :cnt_b[s]]), s
+        assert not got[s, cnt_b[s]:].any()
+
