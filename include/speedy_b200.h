@@ -18,6 +18,7 @@
 #ifndef SPEEDY_B200_H_
 #define SPEEDY_B200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -245,6 +246,13 @@ const char* speedyBatchBuildInfo(void);
 int speedyBatchSynthDevice(int16_t* d_out, uint64_t first_id, int32_t num_streams,
                            int32_t sample_rate, int32_t channels, int64_t frames,
                            void* cuda_stream);
+
+/* Page-locked host buffers for speedyBatchProcess / Write / Read (what cudaHostAlloc
+ * gives, without making the client link the CUDA runtime).  write_combined = 1 suits an
+ * INPUT buffer the host only writes (the device reads it without cache snoops); never
+ * use it for a buffer the host reads.  Returns NULL on failure. */
+void* speedyBatchHostAlloc(size_t bytes, int write_combined);
+void speedyBatchHostFree(void* p);
 
 #ifdef __cplusplus
 }

@@ -75,6 +75,8 @@ def lib():
         "speedyBatchKernelLaunches": (C.c_int64, []),
         "speedyBatchBuildInfo": (C.c_char_p, []),
         "speedyBatchSynthDevice": (C.c_int, [i16p, C.c_uint64, C.c_int32, C.c_int32, C.c_int32, C.c_int64, vp]),
+        "speedyBatchHostAlloc": (C.c_void_p, [C.c_size_t, C.c_int]),
+        "speedyBatchHostFree": (None, [C.c_void_p]),
         # Sonic / Speedy drop-in
         "sonicCreateStream": (vp, [C.c_int, C.c_int]),
         "sonicDestroyStream": (None, [vp]),
@@ -299,3 +301,19 @@ def synth_device(d_out, first_id, num_streams, rate, channels, frames, stream=No
 
 def kernel_launches():
     return lib().speedyBatchKernelLaunches()
+
+
+def host_alloc(shape, dtype=np.int16, write_combined=False):
+    """Page-locked numpy array from speedyBatchHostAlloc (free with host_free(arr))."""
+    nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = lib().speedyBatchHostAlloc(nbytes, int(write_combined))
+    if not p:
+        raise RuntimeError("speedyBatchHostAlloc failed: " + last_error())
+    buf = (C.c_char * nbytes).from_address(p)
+    arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
+    return arr
+
+
+def host_free(arr):
+    lib().speedyBatchHostFree(arr.ctypes.data)
+

@@ -1281,6 +1281,21 @@ int speedyBatchGetTaps(speedyBatch b, int64_t max_frames, int32_t* n_analysis, i
   return 1;
 }
 
+void* speedyBatchHostAlloc(size_t bytes, int write_combined) {
+  void* p = nullptr;
+  const unsigned flags = cudaHostAllocPortable | (write_combined ? cudaHostAllocWriteCombined : 0u);
+  if (cudaHostAlloc(&p, bytes, flags) != cudaSuccess) {
+    cudaGetLastError();
+    set_error("speedyBatchHostAlloc: cudaHostAlloc failed");
+    return nullptr;
+  }
+  return p;
+}
+
+void speedyBatchHostFree(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
 int speedyBatchSynthDevice(int16_t* d_out, uint64_t first_id, int32_t num_streams, int32_t sample_rate,
                            int32_t channels, int64_t frames, void* cuda_stream) {
   if (!d_out || num_streams < 1 || frames < 1) return 0;
