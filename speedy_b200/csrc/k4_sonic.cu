@@ -21,10 +21,21 @@
 // per second of audio and parallelism comes from the streams.  With thousands of
 // streams per GPU one warp per stream is the efficient shape: no block barrier, the
 // uniform bookkeeping executed once.  With few streams (the 1024-stream benchmark
-// leaves 7 per SM) the chain's latency is what is measured, and 2 or 4 warps share
+// leaves 7 per SM) the chain's latency is what is measured; 2 or 4 warps can share
 // the parallel loops of a stream (window refill, decimation, AMDF blocks, overlap-
-// add); all warps run the same uniform control flow on replicated scalar state and
-// meet at three barriers per pitch iteration.
+// add): all warps run the same uniform control flow on replicated scalar state and
+// meet at three barriers per pitch iteration.  Measured at 1024 streams that does not
+// pay (K4 18.5 ms with one warp, 23.1 / 33.2 ms with two / four: the replicated scalar
+// code and the barriers cost more than the split loops save), so one warp per stream
+// is the default everywhere and the wider shapes stay selectable per batch
+// (threads_per_stream; the single-stream drop-in API uses four).
+//
+// Variants.  CH = 1 is a mono specialisation (the multi-channel paths drop out of the
+// instruction stream: the chain is sensitive to instruction-cache misses).  Short
+// launches (10 ms streaming writes, flush) take HOSTMAP = true: the lane assignment of
+// the two searches is computed by the launcher, because the kernel's own set-up would
+// be half of such a launch's instructions.  The shared window is sized by the launcher
+// so that one wave of streams stays resident (k4_buf_frames).
 //
 // Sonic's input FIFO is never materialised: the stream keeps two absolute
 // cursors (head = first unconsumed frame, fed = one past the last frame handed
