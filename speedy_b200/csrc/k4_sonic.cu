@@ -156,19 +156,6 @@ struct Sonic {
     T_END(7);
   }
 
-  // Truncating num / n for |num| < 2^25, 0 < n < 2^11: the float quotient is within
-  // one of the true one, two fix-up steps make it exact.
-  static __device__ __forceinline__ int div_trunc(int num, int n, float rcp_n) {
-    const int an = abs(num);
-    int q = (int)((float)an * rcp_n);
-    int rem = an - q * n;
-    if (rem < 0) { q--; rem += n; }
-    if (rem < 0) { q--; rem += n; }
-    if (rem >= n) { q++; rem -= n; }
-    if (rem >= n) { q++; }
-    return num < 0 ? -q : q;
-  }
-
   // out[t] = (down[t]*(n-t) + up[t]*t) / n per channel, C integer arithmetic.
   // down/up are absolute frames inside the window.
   __device__ __forceinline__ void overlap_add(int n, long long down, long long up, int out_offset_frames) {
