@@ -76,7 +76,13 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks and throttle reasons during the timed region."""
+    """nvidia-smi clocks and throttle reasons during the timed region.
+
+    nvidia-smi needs a few hundred ms to start (longer on an 8-GPU box), more than a
+    short timed region lasts, so the sampler is started before the warm-up steps, stamps
+    every line on arrival and reports the lines that fall inside [t0, t1]; if the region
+    was too short to catch one, the nearest lines taken under the same load (warm-up
+    steps right before it) are used and the result says so."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -91,7 +97,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except Exception:
@@ -99,32 +105,53 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
-    def stop(self):
+    def wait_first(self, timeout=10.0):
+        """Block until nvidia-smi has delivered its first line (or give up)."""
+        t_end = time.time() + timeout
+        while self.proc and not self.lines and time.time() < t_end:
+            time.sleep(0.02)
+
+    def stop(self, t0=None, t1=None):
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for line in self.lines:
+        rows = []
+        for ts, line in self.lines:
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
+                rows.append((ts, float(f[1]), float(f[2]), f[5:9]))
             except ValueError:
                 continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+        note = None
+        use = rows
+        if t0 is not None and t1 is not None:
+            use = [r for r in rows if t0 <= r[0] <= t1]
+            if not use and rows:
+                # the region was shorter than the sampling period: the lines nearest to it
+                mid = 0.5 * (t0 + t1)
+                use = sorted(rows, key=lambda r: abs(r[0] - mid))[:3]
+                note = "timed region shorter than the sampling period: nearest samples under the same load"
+        sm = [r[1] for r in use]
+        mx = [r[2] for r in use]
+        reasons = set()
+        for r in use:
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
         load = [x for x in sm if x > 0]
-        return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        out = {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": max(mx) if mx else None,
+               "samples": len(sm), "reasons": sorted(reasons)}
+        if note:
+            out["note"] = note
+        return out
 
 
 # --------------------------------------------------------------------------
@@ -234,28 +261,37 @@ def run_cuda_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # the clock sampler runs from before the warm-up (nvidia-smi is slow to start): the
+    # warm-up steps keep the GPU under the same load until its first line has arrived
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
+    if not sampler.lines:
+        sampler.wait_first()
+        for _ in range(3):
+            step()
+        barrier()
 
     # ---- timed region: K steps, device-resident input ----------------------
     batch.set_profiling(True)
-    sampler = ClockSampler(local)
-    sampler.start()
     launches0 = sb.kernel_launches()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ktimes = []
     barrier()
+    wall0 = time.time()
     ev0.record()
     for _ in range(args.steps):
         step()
     ev1.record()
     barrier()
+    wall1 = time.time()
     launches = sb.kernel_launches() - launches0
     elapsed_ms = ev0.elapsed_time(ev1)
     kt_sum = batch.kernel_times()  # summed over the K timed steps
     ktimes.append({k: v / args.steps for k, v in kt_sum.items()})
-    clocks = sampler.stop()
+    clocks = sampler.stop(wall0, wall1)
     batch.set_profiling(False)
 
     # output size of one step (for the algorithmic bytes)
