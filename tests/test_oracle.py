@@ -289,6 +289,23 @@ def test_reference_schedule_is_chunk_invariant(golden_inputs, chunk):
     assert np.array_equal(a["speed"], b["speed"]) and np.array_equal(a["out"], b["out"])
 
 
+@pytest.mark.parametrize("rate,kind,match_matlab,fft_double", [(44100, "fftw", False, True), (44100, "kiss", True, False),
+                                                               (11025, "fftw", False, True), (32000, "kiss", True, False)])
+def test_port_equals_reference_at_prime_and_odd_windows(rate, kind, match_matlab, fft_double):
+    """44.1 kHz has a prime 661-sample window (N = 1322 = 2 * 661), 11.025 kHz an odd one:
+    the FFT restatement's generic butterfly (oracle/fft_oracle.c) carries them; the port
+    still equals the reference's own code bit for bit there."""
+    if not ol.ref_available(kind):
+        pytest.skip("oracle/_ref not built")
+    pcm = ol.synth(11, 1, rate, 1, rate)[0]
+    r = ol.ref_process(kind, pcm, rate, 1, 2.0, 1.0, 0.1, chunk=1000)
+    p = ol.port_process(ol.cfg(rate, 1, 2.0, 1.0, 0.1, match_matlab, fft_double), pcm)
+    assert np.array_equal(r["spectrogram"], p["spectrogram"])
+    assert np.array_equal(r["tension"], p["tension"])
+    assert np.array_equal(r["speed"], p["speed"])
+    assert np.array_equal(r["out"], p["out"])
+
+
 def test_port_stereo_equals_reference():
     if not ol.ref_available("fftw"):
         pytest.skip("oracle/_ref not built")
