@@ -530,7 +530,10 @@ struct Sonic {
   // processStreamInput with the speed that is current now.
   __device__ __forceinline__ void process(float speed) {
     const long long numInput = fed - head;
-    if ((double)speed > 1.00001 || (double)speed < 0.99999) {
+    // upstream: speed > 1.00001 || speed < 0.99999 with speed promoted to double; the same
+    // test on the float itself: 0x3F800054 is the smallest float above 1.00001, 0x3F7FFF58
+    // the largest below 0.99999
+    if (speed >= __uint_as_float(0x3F800054u) || speed <= __uint_as_float(0x3F7FFF58u)) {
       if (numInput < maxReq) return;
       long long position = 0;
       do {
