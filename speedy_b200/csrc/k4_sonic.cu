@@ -351,13 +351,13 @@ struct Sonic {
   }
 
   // floor(a / b) for a < 2^27, 0 < b < 2^11 (quotient < 2^16): float estimate + fix-up.
+  // The estimate carries three roundings of 2^-24 each, under 0.02 at that size of
+  // quotient, so its truncation is off by at most one either way.
   static __device__ __forceinline__ int udiv_small(unsigned a, int b) {
     int q = (int)((float)a * __frcp_rn((float)b));
-    int rem = (int)a - q * b;
-    if (rem < 0) { q--; rem += b; }
-    if (rem < 0) { q--; rem += b; }
-    if (rem >= b) { q++; rem -= b; }
-    if (rem >= b) { q++; }
+    const int rem = (int)a - q * b;
+    if (rem < 0) q--;
+    else if (rem >= b) q++;
     return q;
   }
 
