@@ -104,6 +104,7 @@ struct Sonic {
   // coarse-pass lane mapping: group cGi (-1 = idle), sub-lane cSub of cG, largest cG
   int cGi, cSub, cG, cMaxG;
   unsigned dec_magic;
+  const unsigned* magic_tab;  // ceil(2^(32+s) / n) for n = 2 .. maxP, or null (computed on demand)
   bool timing;
 
   // channel count: a compile-time constant in the mono specialisation (CH = 1)
@@ -156,6 +157,13 @@ struct Sonic {
     T_END(7);
   }
 
+  // ceil(2^(32+shift) / n) for 2^shift < n <= 2^(shift+1): floor from the correctly rounded
+  // double quotient (the true one is at least 1/n away from the integers it does not hit)
+  static __device__ __forceinline__ unsigned division_magic(int n, int shift) {
+    const double qd = __ddiv_rn((double)(1ULL << (32 + shift)), (double)n);
+    return (unsigned)(unsigned long long)qd + ((n & (n - 1)) ? 1u : 0u);
+  }
+
   // out[t] = (down[t]*(n-t) + up[t]*t) / n per channel, C integer arithmetic.
   // down/up are absolute frames inside the window.
   __device__ __forceinline__ void overlap_add(int n, long long down, long long up, int out_offset_frames) {
@@ -171,8 +179,7 @@ struct Sonic {
     int shift = 0;
     if (n > 1) {
       shift = 31 - __clz(n - 1);
-      const double qd = __ddiv_rn((double)(1ULL << (32 + shift)), (double)n);
-      magic = (unsigned)(unsigned long long)qd + ((n & (n - 1)) ? 1u : 0u);
+      magic = (magic_tab && n <= maxP) ? magic_tab[n] : division_magic(n, shift);
     }
     if (nch() == 1) {
       if (n == 1) {
@@ -602,6 +609,7 @@ __host__ __device__ inline size_t k4_stream_smem(const Geometry& g, int buf_fram
   size_t b = (size_t)(buf_frames + kPad) * sizeof(int);
   b += (size_t)((g.max_required / g.skip + kPad + 3) & ~3) * sizeof(int);
   b += (size_t)2 * 4 * kMaxGroups * sizeof(unsigned);
+  b += (size_t)((g.max_period + 4) & ~3) * sizeof(unsigned);  // overlap-add division constants
   if (g.channels > 1) b += (size_t)buf_frames * g.channels * sizeof(short) + 16;  // + one vector of over-read
   return (b + 15) & ~(size_t)15;
 }
@@ -641,7 +649,16 @@ __global__ void __launch_bounds__(NW * 32, MINB) k4_sonic(K4Params p) {
   k.w32 = reinterpret_cast<int*>(smem_raw);
   k.ds32 = k.w32 + k.bufN + kPad;
   k.sums = reinterpret_cast<unsigned*>(k.ds32 + ((k.maxReq / k.skip + kPad + 3) & ~3));
-  k.buf = reinterpret_cast<short*>(k.sums + 2 * 4 * kMaxGroups);
+  unsigned* magic_tab = k.sums + 2 * 4 * kMaxGroups;  // [(maxP + 4) & ~3]
+  k.buf = reinterpret_cast<short*>(magic_tab + ((k.maxP + 4) & ~3));
+  // long launches: the overlap-add's division constants once, off the splice chain (a
+  // double division per pitch iteration otherwise); short ones compute the few they need
+  k.magic_tab = HOSTMAP ? nullptr : magic_tab;
+  if (!HOSTMAP) {
+    for (int n = 2 + k.vl; n <= k.maxP; n += Sonic<NW, CH>::VL) {
+      magic_tab[n] = Sonic<NW, CH>::division_magic(n, 31 - __clz(n - 1));
+    }
+  }
   k.bufStart = 0;
   k.bufLen = 0;
   k.dec_magic = (unsigned)((0x100000000ULL + (unsigned)(g.channels * k.skip) - 1) / (unsigned)(g.channels * k.skip));
