@@ -372,18 +372,19 @@ struct Sonic {
   // worst candidates; lags ascend, so strict comparisons reproduce the C scan.
   __device__ __forceinline__ void fold(const unsigned (&d)[4], int pg, int lo, int hi, unsigned& bd, int& bp,
                                        unsigned& wd, int& wp) {
+    // branch-free: the splice chain waits for this, and only a few lanes hold sums
 #pragma unroll
     for (int l = 0; l < 4; l++) {
       const int p = pg + l;
-      if (p >= lo && p <= hi) {
-        if (bp == 0) {
-          bd = wd = d[l];
-          bp = wp = p;
-        } else {
-          if ((unsigned long long)d[l] * (unsigned)bp < (unsigned long long)bd * (unsigned)p) { bd = d[l]; bp = p; }
-          if ((unsigned long long)d[l] * (unsigned)wp > (unsigned long long)wd * (unsigned)p) { wd = d[l]; wp = p; }
-        }
-      }
+      const bool in = p >= lo && p <= hi;
+      const bool first = bp == 0;
+      const bool lt = (unsigned long long)d[l] * (unsigned)bp < (unsigned long long)bd * (unsigned)p;
+      const bool gt = (unsigned long long)d[l] * (unsigned)wp > (unsigned long long)wd * (unsigned)p;
+      const bool tb = in && (first || lt), tw = in && (first || gt);
+      bd = tb ? d[l] : bd;
+      bp = tb ? p : bp;
+      wd = tw ? d[l] : wd;
+      wp = tw ? p : wp;
     }
   }
 
