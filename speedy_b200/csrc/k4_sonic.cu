@@ -361,11 +361,9 @@ struct Sonic {
   // The estimate carries three roundings of 2^-24 each, under 0.02 at that size of
   // quotient, so its truncation is off by at most one either way.
   static __device__ __forceinline__ int udiv_small(unsigned a, int b) {
-    int q = (int)((float)a * __frcp_rn((float)b));
+    const int q = (int)((float)a * __frcp_rn((float)b));
     const int rem = (int)a - q * b;
-    if (rem < 0) q--;
-    else if (rem >= b) q++;
-    return q;
+    return q + (rem >= b ? 1 : 0) - (rem < 0 ? 1 : 0);
   }
 
   // Fold the four lag sums a lane holds (lags pg .. pg+3) into its running best /
@@ -526,10 +524,8 @@ struct Sonic {
       }
     }
     // prevPeriodBetter(preferNew = 1)
-    int result = period;
-    if (minDiff != 0 && prevPeriod != 0) {
-      if (!(maxDiff > minDiff * 3) && !(minDiff * 2 <= prevMinDiff * 3)) result = prevPeriod;
-    }
+    const bool keep_prev = minDiff != 0 && prevPeriod != 0 && !(maxDiff > minDiff * 3) && !(minDiff * 2 <= prevMinDiff * 3);
+    const int result = keep_prev ? prevPeriod : period;
     prevMinDiff = minDiff;
     prevPeriod = period;
     return result;
