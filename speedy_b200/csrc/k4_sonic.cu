@@ -105,6 +105,7 @@ struct Sonic {
   int cGi, cSub, cG, cMaxG;
   unsigned dec_magic;
   const unsigned* magic_tab;  // ceil(2^(32+s) / n) for n = 2 .. maxP, or null (computed on demand)
+  bool fold_all;  // few streams per SM (latency bound): every lane runs the fold rather than branching around it
   bool timing;
 
   // channel count: a compile-time constant in the mono specialisation (CH = 1)
@@ -428,9 +429,13 @@ struct Sonic {
         for (int l = 0; l < 4; l++) d[l] += e[l];
       }
       combine(d, cSub, cG, cMaxG);
-      if (cGi >= 0 && cSub == 0) {
-        if (NW == 1) fold(d, pg, lo, hi, bd, bp, wd, wp);
-        else *reinterpret_cast<uint4*>(tot + 4 * cGi) = make_uint4(d[0], d[1], d[2], d[3]);
+      if (NW == 1) {
+        // every lane runs the (branch-free) fold; only a group's first lane has a range
+        const bool leader = cGi >= 0 && cSub == 0;
+        if (fold_all) fold(d, pg, leader ? lo : 1, leader ? hi : 0, bd, bp, wd, wp);
+        else if (leader) fold(d, pg, lo, hi, bd, bp, wd, wp);
+      } else if (cGi >= 0 && cSub == 0) {
+        *reinterpret_cast<uint4*>(tot + 4 * cGi) = make_uint4(d[0], d[1], d[2], d[3]);
       }
     } else {
       // blocks of group gi: j = 0 .. nblk-1 at B0 + 4j; fully valid for jf0 <= j < jf1,
@@ -460,10 +465,13 @@ struct Sonic {
           for (int l = 0; l < 4; l++) d[l] += e[l];
         }
         combine(d, fg, fG, fG);
-        if (live && fg == 0) {
+        if (NW == 1) {
           // (one warp: rounds ascend, so the running candidates see ascending lags)
-          if (NW == 1) fold(d, pg, lo, hi, bd, bp, wd, wp);
-          else *reinterpret_cast<uint4*>(tot + 4 * gi) = make_uint4(d[0], d[1], d[2], d[3]);
+          const bool leader = live && fg == 0;
+          if (fold_all) fold(d, pg, leader ? lo : 1, leader ? hi : 0, bd, bp, wd, wp);
+          else if (leader) fold(d, pg, lo, hi, bd, bp, wd, wp);
+        } else if (live && fg == 0) {
+          *reinterpret_cast<uint4*>(tot + 4 * gi) = make_uint4(d[0], d[1], d[2], d[3]);
         }
       }
     }
@@ -651,6 +659,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k4_sonic(K4Params p) {
   // long launches: the overlap-add's division constants once, off the splice chain (a
   // double division per pitch iteration otherwise); short ones compute the few they need
   k.magic_tab = HOSTMAP ? nullptr : magic_tab;
+  k.fold_all = MINB == 1;
   if (!HOSTMAP) {
     for (int n = 2 + k.vl; n <= k.maxP; n += Sonic<NW, CH>::VL) {
       magic_tab[n] = Sonic<NW, CH>::division_magic(n, 31 - __clz(n - 1));
