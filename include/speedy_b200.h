@@ -229,6 +229,7 @@ int speedyBatchGetTaps(speedyBatch batch, int64_t max_frames,
 #define SPEEDY_STATUS_FLUSHED 2
 #define SPEEDY_STATUS_INPUT_OVERFLOW 4  /* Sonic FIFO outgrew the history */
 #define SPEEDY_STATUS_READ_TRUNCATED 8
+#define SPEEDY_STATUS_SPLICE_STALLED 16 /* a speed left no room for one output sample per pitch period */
 int speedyBatchGetStatus(speedyBatch batch, int32_t* status);
 
 /* Frame geometry for a sample rate (speedy.c:213-214, 335-338). */

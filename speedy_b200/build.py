@@ -24,6 +24,7 @@ UNITS = [
     ("k1_spectral.cu", []),
     ("k2_tension.cu", ["--fmad=false"]),
     ("k4_sonic.cu", ["--fmad=false"]),
+    ("k4_splice.cu", ["--fmad=false"]),
     ("batch.cu", ["--fmad=false"]),
     ("sonic_api.cpp", []),
 ]

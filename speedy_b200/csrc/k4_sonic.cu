@@ -63,6 +63,7 @@ __device__ unsigned long long g_k4_cycles[16];
 
 namespace {
 
+
 #ifdef K4_TIMING
 #define T_BEGIN() const long long _t0 = clock64()
 #define T_END(slot) do { if (vl == 0 && timing) atomicAdd(&g_k4_cycles[slot], (unsigned long long)(clock64() - _t0)); } while (0)
@@ -826,6 +827,9 @@ __global__ void __launch_bounds__(NW * 32, MINB) k4_sonic(K4Params p) {
         k.outTotal = expected;
         k.outCount = k.outCount > excess ? (int)(k.outCount - excess) : 0;
       }
+      // the padding is not input: the stream carries on from the real end of the data
+      // (upstream sonicFlushStream leaves numInputSamples = 0 and stays usable)
+      k.fed -= 2 * k.maxReq;
       k.head = k.fed;
       k.remCopy = 0;
       k.status |= 2;  // SPEEDY_STATUS_FLUSHED
@@ -858,7 +862,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k4_sonic(K4Params p) {
 //   ceil((q + 1) / T) adjacent lanes with the smallest T that fits 32 lanes.
 //   fine (and single-stage) pass: fG adjacent lanes per group, groups never straddle a
 //   warp: the largest fG with NW * (32 / fG) >= the group count.
-static void k4_lane_map(K4Params& p, int NW) {
+void k4_lane_map(K4Params& p, int NW) {
   const Geometry& g = p.g;
   const int c_lo = g.min_period / g.skip, c_hi = g.max_period / g.skip;
   const int qlo = c_lo >> 2, qhi = c_hi >> 2;
@@ -952,6 +956,16 @@ static cudaError_t launch_k4_t(K4Params& p, cudaStream_t stream) {
 }
 
 cudaError_t launch_k4(const K4Params& p0, cudaStream_t stream) {
+  // long writes of mono streams take the pipelined shape (k4_splice.cu); flushes, short
+  // launches (10 ms streaming writes) and multi-channel streams stay here
+  {
+    static const int legacy = getenv("SPEEDY_K4_LEGACY") ? atoi(getenv("SPEEDY_K4_LEGACY")) : 0;
+    static const long long min_frames = getenv("SPEEDY_K4_SPLICE_MIN") ? atoll(getenv("SPEEDY_K4_SPLICE_MIN")) : -1;
+    const bool short_launch = p0.flush || p0.frames - p0.done <= (min_frames >= 0 ? min_frames : (long long)p0.g.rate);
+    if (!legacy && !short_launch && p0.threads_per_stream <= 32 && k4_splice_supported(p0)) {
+      return launch_k4_splice(p0, stream);
+    }
+  }
   K4Params p = p0;
   p.buf_frames = k4_buf_frames(p.g, p.n_streams);
   // threads per stream: with few streams per SM the serial splice chain is latency

@@ -105,6 +105,9 @@ struct K4Params {
   int c_max_g, f_g, f_per_round;
 };
 cudaError_t launch_k4(const K4Params& p, cudaStream_t stream);
+// the pipelined shape (k4_splice.cu): chain / filler / output warps per stream
+bool k4_splice_supported(const K4Params& p);
+cudaError_t launch_k4_splice(const K4Params& p, cudaStream_t stream);
 
 // ---- bookkeeping after a write: carry the input tail, advance totals ------
 struct TailParams {
