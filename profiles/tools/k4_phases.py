@@ -32,6 +32,7 @@ for i, nm in enumerate(names):
     table['phases'][nm] = {'cycles': int(out[i]), 'share': float(out[i]) / tot, 'per_iteration': float(out[i]) / max(it, 1)}
 other = tot - int(out[:8].sum())
 table['phases']['other'] = {'cycles': other, 'share': other / tot, 'per_iteration': other / max(it, 1)}
+table['window_chunks_waited'] = int(out[11]); table['window_chunks_not_ready'] = int(out[12])
 print(json.dumps(table, indent=1))
 if dst:
     json.dump(table, open(dst, 'w'), indent=1)

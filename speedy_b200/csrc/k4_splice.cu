@@ -58,9 +58,11 @@ constexpr int kThreads = 96;
 
 enum { REC_SKIP = 0, REC_INSERT = 1, REC_COPY = 2, REC_EXIT = 3 };
 
-// Shared-memory carve-up (byte offsets, multiples of 16), filled by the launcher.
+// Shared-memory carve-up (byte offsets, multiples of 16): computed by the launcher, and at
+// compile time for the 16 kHz instantiation (every address in its splice loop is then the
+// shared window's base plus a constant).
 struct SpliceLayout {
-  int bars, ctrl, recs, rcp, magic, ds, win, raw, oring, total;
+  int bars, ctrl, recs, rcp, magic, ds, part, win, raw, oring, total;
   int nsr;       // raw ring slots (chunks)
   int nsw;       // window ring slots
   int rw;        // window ring frames = nsw * kCF
@@ -69,7 +71,51 @@ struct SpliceLayout {
   int or_elems;  // output ring, int16 elements (power of two)
   int depth;     // chunks of bulk copies in flight ahead of the chunk being widened
   int out_vec;   // 1: the stream's output rows take 16-byte stores
+  int poll_ns;   // back-off between the filler's / output role's polls of a barrier
 };
+
+constexpr int kDepthDefault = 6, kWindowAhead = 3;
+
+__host__ __device__ constexpr int lay_take(int& off, int bytes) {
+  const int at = off;
+  off += (bytes + 15) & ~15;
+  return at;
+}
+
+__host__ __device__ constexpr SpliceLayout make_layout(int max_period, int max_required, int skip, int channels,
+                                                       int depth, int nsw_override) {
+  SpliceLayout L{};
+  const int span = max_required + kPadW;  // what one search needs in the window
+  const int span_chunks = (span + kCF - 1) / kCF;
+  L.depth = depth;
+  L.nsr = span_chunks + 1 + depth + 1;
+  L.nsw = nsw_override > 0 ? nsw_override : span_chunks + 1 + kWindowAhead;
+  L.rw = L.nsw * kCF;
+  L.rr = L.nsr * kCF;
+  L.mir = (span + 15) & ~15;
+  int or_elems = 1024;
+  while (or_elems < max_required * channels + 64) or_elems <<= 1;
+  L.or_elems = or_elems;
+  L.out_vec = 0;
+  L.poll_ns = 500;
+  int off = 0;
+  L.bars = lay_take(off, (2 * L.nsr + 2 * L.nsw + kQ) * 8);
+  L.ctrl = lay_take(off, 16);
+  L.recs = lay_take(off, kQ * 16);
+  L.rcp = lay_take(off, ((max_period + 8) & ~3) * 4);
+  L.magic = lay_take(off, ((max_period + 4) & ~3) * 4);
+  L.ds = lay_take(off, (max_required / skip + 32 + 16) * 4);
+  L.part = lay_take(off, 7 * 64 * 4);  // per-lag partial sums: 4 rows (coarse) + 3 rows (fine) of 64 lags
+  L.win = lay_take(off, (L.rw + L.mir) * 4);
+  L.raw = lay_take(off, L.rr * channels * 2);
+  L.oring = lay_take(off, L.or_elems * 2);
+  L.total = off;
+  return L;
+}
+
+constexpr SpliceLayout kLay16 = make_layout(246, 492, 4, 1, kDepthDefault, 0);  // 16 kHz mono
+
+extern __shared__ __align__(128) unsigned char splice_smem[];
 
 // ---- mbarrier / bulk-copy primitives (PTX) ---------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -249,14 +295,24 @@ __device__ __forceinline__ Plan make_plan(const K4Params& p, int s) {
 // ---------------------------------------------------------------------------
 template <bool K16>
 struct Chain {
-  // shared memory
-  int* win;
-  int* ds;
-  const float* rcp;
-  uint64_t *wfull, *wempty, *qfull;
-  int4* recs;
-  int* ctrl;  // [0] records the output role has finished
-  int rw, nsw;
+  // shared memory: byte offsets of the generic instantiation (constants for 16 kHz)
+  int o_win, o_ds, o_rcp, o_recs, o_ctrl, o_wempty, o_qfull;
+  int rw_, nsw_;
+  __device__ __forceinline__ int* win() const { return reinterpret_cast<int*>(splice_smem + (K16 ? kLay16.win : o_win)); }
+  __device__ __forceinline__ int* ds() const { return reinterpret_cast<int*>(splice_smem + (K16 ? kLay16.ds : o_ds)); }
+  __device__ __forceinline__ float* rcp() const { return reinterpret_cast<float*>(splice_smem + (K16 ? kLay16.rcp : o_rcp)); }
+  __device__ __forceinline__ int4* recs() const { return reinterpret_cast<int4*>(splice_smem + (K16 ? kLay16.recs : o_recs)); }
+  // [0] records the output role has finished, [1] chain done, [2] window chunks widened
+  __device__ __forceinline__ int* ctrl() const { return reinterpret_cast<int*>(splice_smem + (K16 ? kLay16.ctrl : o_ctrl)); }
+  __device__ __forceinline__ uint64_t* wempty() const {
+    return reinterpret_cast<uint64_t*>(splice_smem + (K16 ? kLay16.bars + (2 * kLay16.nsr + kLay16.nsw) * 8 : o_wempty));
+  }
+  __device__ __forceinline__ uint64_t* qfull() const {
+    return reinterpret_cast<uint64_t*>(splice_smem + (K16 ? kLay16.bars + (2 * kLay16.nsr + 2 * kLay16.nsw) * 8 : o_qfull));
+  }
+  __device__ __forceinline__ unsigned* part() const { return reinterpret_cast<unsigned*>(splice_smem + kLay16.part); }
+  __device__ __forceinline__ int rw() const { return K16 ? kLay16.rw : rw_; }
+  __device__ __forceinline__ int nsw() const { return K16 ? kLay16.nsw : nsw_; }
   // geometry
   int S, minP, maxP, maxReq, skip;
   int c_lo, c_hi, ds_count;  // coarse lag range, decimated values per search
@@ -400,6 +456,32 @@ __device__ __noinline__ void resolve_exact(unsigned d0, unsigned d1, unsigned d2
   *rp = bp;
 }
 
+// The same for the one-lag-per-lane form: lane i holds the sums of lags base + i (sa) and
+// base + 32 + i (sb); candidates are ballots.
+__device__ __noinline__ void resolve_exact2(unsigned sa, unsigned sb, unsigned bal_a, unsigned bal_b, int base,
+                                            int want_min, unsigned* rd, int* rp) {
+  unsigned bd = 0u;
+  int bp = want_min ? 0 : 255;
+#pragma unroll 1
+  for (int half = 0; half < 2; half++) {
+    unsigned bal = half ? bal_b : bal_a;
+    while (bal) {
+      const int src = __ffs(bal) - 1;
+      bal &= bal - 1;
+      const unsigned cd = __shfl_sync(kFull, half ? sb : sa, src);
+      const int cp = base + 32 * half + src;
+      const unsigned long long lhs = (unsigned long long)cd * (unsigned)bp;
+      const unsigned long long rhs = (unsigned long long)bd * (unsigned)cp;
+      if (want_min ? (bp == 0 || lhs < rhs) : (lhs > rhs)) {
+        bd = cd;
+        bp = cp;
+      }
+    }
+  }
+  *rd = bd;
+  *rp = bp;
+}
+
 // floor(a / b) for a < 2^27, 0 < b < 2^11 (quotient < 2^16) from the float reciprocal of b:
 // the estimate is off by at most one either way, one fix-up per side.
 __device__ __forceinline__ int udiv_small(unsigned a, int b, float rcp_b) {
@@ -437,6 +519,62 @@ __device__ __forceinline__ int search(const Chain<K16>& k, const int* arr, int o
     if (sub == 0 && hd) block_head(base, pg, hd, d);
     if (sub == (G > 1 ? 1 : 0)) block_tail(base + 4 * jf1, pg, hd, d);
   }
+  if (K16) {
+    // 16 kHz: the partial sums go through shared memory, one row per lane of a group, and come
+    // back one lag per lane (lag base + lane, and base + 32 + lane): no shuffle tree, no
+    // four-lags-per-leader selects.  Rows a group has no lane for stay zero (coarse pass: the
+    // lane assignment is static); lags outside [lo, hi] are masked below.
+    constexpr int ROWS = MAXG;
+    unsigned* part = k.part() + (WANT_DIFFS ? 4 * 64 : 0);
+    const int base = lo & ~3;
+    if (live) *reinterpret_cast<uint4*>(part + sub * 64 + (pg - base)) = make_uint4(d[0], d[1], d[2], d[3]);
+    __syncwarp();
+    unsigned sa = 0u, sb = 0u;
+#pragma unroll
+    for (int r = 0; r < ROWS; r++) {
+      sa += part[r * 64 + k.lane];
+      sb += part[r * 64 + 32 + k.lane];
+    }
+    __syncwarp();  // (the next search of this kind rewrites the rows)
+    const int la = base + k.lane, lb = la + 32;
+    const bool va = la >= lo && la <= hi, vb = lb <= hi;
+    const float ka = __uint2float_rn(sa) * k.rcp()[va ? la : 0], kb = __uint2float_rn(sb) * k.rcp()[vb ? lb : 0];
+    const float big = 3.0e38f;
+    const float emin = __uint_as_float(__reduce_min_sync(kFull, __float_as_uint(fminf(va ? ka : big, vb ? kb : big))));
+    const float tmin = emin * 1.000002f;
+    const unsigned bal_a = __ballot_sync(kFull, va && ka <= tmin), bal_b = __ballot_sync(kFull, vb && kb <= tmin);
+    unsigned wal_a = 0u, wal_b = 0u;
+    float emax = 1.0f;
+    if (WANT_DIFFS) {
+      emax = __uint_as_float(__reduce_max_sync(kFull, __float_as_uint(fmaxf(va ? ka : 0.f, vb ? kb : 0.f))));
+      const float tmax = emax * 0.999998f;
+      wal_a = __ballot_sync(kFull, va && ka >= tmax);
+      wal_b = __ballot_sync(kFull, vb && kb >= tmax);
+    }
+    unsigned best_diff, worst_diff = 0u;
+    int best, worst = 255;
+    const bool one_min = __popc(bal_a) + __popc(bal_b) == 1;
+    const bool one_max = !WANT_DIFFS || (__popc(wal_a) + __popc(wal_b) == 1 && emax > 0.f);
+    if (one_min && one_max) {
+      const int src = __ffs(bal_a | bal_b) - 1;
+      best = base + src + (bal_a ? 0 : 32);
+      best_diff = __shfl_sync(kFull, bal_a ? sa : sb, src);
+      if (WANT_DIFFS) {
+        const int srw = __ffs(wal_a | wal_b) - 1;
+        worst = base + srw + (wal_a ? 0 : 32);
+        worst_diff = __shfl_sync(kFull, wal_a ? sa : sb, srw);
+      }
+    } else {
+      resolve_exact2(sa, sb, bal_a, bal_b, base, 1, &best_diff, &best);
+      if (WANT_DIFFS) resolve_exact2(sa, sb, wal_a, wal_b, base, 0, &worst_diff, &worst);
+    }
+    if (WANT_DIFFS) {
+      const int md = udiv_small(best_diff, best, k.rcp()[best]);
+      *minDiff = md;
+      *maxDiff = worst_diff >= (unsigned)(3 * md + 1) * (unsigned)worst ? 3 * md + 1 : 0;
+    }
+    return best;
+  }
   // the group's first lane collects its neighbours' partial sums (independent shuffles)
   {
     const unsigned o0 = d[0], o1 = d[1], o2 = d[2], o3 = d[3];
@@ -460,7 +598,7 @@ __device__ __forceinline__ int search(const Chain<K16>& k, const int* arr, int o
     }
   }
   const bool leader = live && sub == 0;
-  const float4 r4 = leader ? *reinterpret_cast<const float4*>(k.rcp + pg) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 r4 = leader ? *reinterpret_cast<const float4*>(k.rcp() + pg) : make_float4(0.f, 0.f, 0.f, 0.f);
   // float keys of this lane's lags inside [lo, hi]
   const bool v0 = leader && pg >= lo && pg <= hi;
   const bool v1 = leader && pg + 1 >= lo && pg + 1 <= hi;
@@ -506,7 +644,7 @@ __device__ __forceinline__ int search(const Chain<K16>& k, const int* arr, int o
     if (WANT_DIFFS) resolve_exact(d[0], d[1], d[2], d[3], pg, cw, 0, &worst_diff, &worst);
   }
   if (WANT_DIFFS) {
-    const int md = udiv_small(best_diff, best, k.rcp[best]);
+    const int md = udiv_small(best_diff, best, k.rcp()[best]);
     *minDiff = md;
     // maxDiff = floor(worst_diff / worst) only ever meets "maxDiff > 3 * minDiff"
     // (oracle/sonic_oracle.c:217), i.e. worst_diff >= (3 * minDiff + 1) * worst: no division.
@@ -527,7 +665,7 @@ __device__ __forceinline__ void decimate(const Chain<K16>& k, int off) {
   __syncwarp();  // every lane is done reading the previous decimated copy
   if (K16) {
     const int r = off & 3;
-    const int4* p = reinterpret_cast<const int4*>(k.win + (off & ~3) + 16 * k.lane);
+    const int4* p = reinterpret_cast<const int4*>(k.win() + (off & ~3) + 16 * k.lane);
     const int4 x0 = p[0], x1 = p[1], x2 = p[2], x3 = p[3], x4 = p[4];
     int s0, s1, s2, s3;
     if (r == 0) {
@@ -549,13 +687,13 @@ __device__ __forceinline__ void decimate(const Chain<K16>& k, int off) {
     o.z = (s2 + ((s2 >> 31) & 3)) >> 2;
     o.w = (s3 + ((s3 >> 31) & 3)) >> 2;
     // 128 values: the few past maxRequired / 4 only ever meet masked samples
-    reinterpret_cast<int4*>(k.ds)[k.lane] = o;
+    reinterpret_cast<int4*>(k.ds())[k.lane] = o;
   } else if ((k.skip & 3) == 0) {
     // aligned 16-byte walk: the first and last vector of a value are partial
     const int count = k.ds_count;
     const int r = off & 3;
     const int nmid = (k.skip >> 2) - 1;
-    const int* base = k.win + (off & ~3);
+    const int* base = k.win() + (off & ~3);
 #pragma unroll 1
     for (int i = k.lane; i < count; i += 32) {
       const int4* p = reinterpret_cast<const int4*>(base + i * k.skip);
@@ -568,18 +706,18 @@ __device__ __forceinline__ void decimate(const Chain<K16>& k, int off) {
         v += (t.x + t.y) + (t.z + t.w);
       }
       const int qa = (int)__umulhi((unsigned)abs(v), k.dec_magic);
-      k.ds[i] = v < 0 ? -qa : qa;
+      k.ds()[i] = v < 0 ? -qa : qa;
     }
   } else {
     const int count = k.ds_count;
 #pragma unroll 1
     for (int i = k.lane; i < count; i += 32) {
       int v = 0;
-      const int* q = k.win + off + i * k.skip;
+      const int* q = k.win() + off + i * k.skip;
 #pragma unroll 1
       for (int j = 0; j < k.skip; j++) v += q[j];
       const int qa = (int)__umulhi((unsigned)abs(v), k.dec_magic);
-      k.ds[i] = v < 0 ? -qa : qa;
+      k.ds()[i] = v < 0 ? -qa : qa;
     }
   }
   __syncwarp();
@@ -597,8 +735,8 @@ __device__ __forceinline__ int find_pitch_period(Chain<K16>& k, int off) {
     decimate<K16>(k, off);
     TS_BEGIN();
     const int cpg = 4 * ((k.gCLo() >> 2) + k.cGi);
-    if (K16) period = search<K16, 4, false, false>(k, k.ds, 0, 10, 61, cpg, k.cGi >= 0, k.cSub, k.cG, 4, nullptr, nullptr);
-    else period = search<K16, 0, false, false>(k, k.ds, 0, k.c_lo, k.c_hi, cpg, k.cGi >= 0, k.cSub, k.cG, k.cMaxG, nullptr, nullptr);
+    if (K16) period = search<K16, 4, false, false>(k, k.ds(), 0, 10, 61, cpg, k.cGi >= 0, k.cSub, k.cG, 4, nullptr, nullptr);
+    else period = search<K16, 0, false, false>(k, k.ds(), 0, k.c_lo, k.c_hi, cpg, k.cGi >= 0, k.cSub, k.cG, k.cMaxG, nullptr, nullptr);
 #ifdef K4_TIMING
     if (k.lane == 0 && k.timing) atomicAdd(&g_k4s_cycles[2], (unsigned long long)(clock64() - _t0 + (period & 0)));
 #endif
@@ -614,8 +752,8 @@ __device__ __forceinline__ int find_pitch_period(Chain<K16>& k, int off) {
     const int g0 = lo >> 2;
     const int pg = 4 * (g0 + k.fGi0);
     const bool live = k.fGi0 < (hi >> 2) - g0 + 1;
-    if (K16) period = search<K16, 3, true, true>(k, k.win, off, lo, hi, pg, live, k.fg, 3, 3, &minDiff, &maxDiff);
-    else period = search<K16, 0, false, true>(k, k.win, off, lo, hi, pg, live, k.fg, k.fG, k.fG, &minDiff, &maxDiff);
+    if (K16) period = search<K16, 3, true, true>(k, k.win(), off, lo, hi, pg, live, k.fg, 3, 3, &minDiff, &maxDiff);
+    else period = search<K16, 0, false, true>(k, k.win(), off, lo, hi, pg, live, k.fg, k.fG, k.fG, &minDiff, &maxDiff);
 #ifdef K4_TIMING
     if (k.lane == 0 && k.timing) atomicAdd(&g_k4s_cycles[4], (unsigned long long)(clock64() - _t0 + (period & 0)));
 #endif
@@ -629,19 +767,17 @@ __device__ __forceinline__ int find_pitch_period(Chain<K16>& k, int off) {
   return result;
 }
 
-// Window chunks up to relative frame `need_end` are filled.
+// Window chunks up to relative frame `need_end` are filled.  The filler publishes the number
+// of chunks it has widened in a shared-memory word (its stores fenced before it): a plain
+// load on the chain's critical path, not a barrier-unit round trip.
 template <bool K16>
 __device__ __forceinline__ void chain_ensure(Chain<K16>& k, int need_end) {
-  TS_BEGIN();
   const int cneed = (need_end - 1) >> kCFShift;
-  while (k.cready <= cneed) {
-    mbar_wait(k.wfull + k.rslot, k.rpar);
-    k.cready++;
-    if (++k.rslot == k.nsw) {
-      k.rslot = 0;
-      k.rpar ^= 1;
-    }
-  }
+  if (k.cready > cneed) return;
+  TS_BEGIN();
+  do {
+    k.cready = ld_volatile_s32(k.ctrl() + 2);
+  } while (k.cready <= cneed);
   TS_END(0);
 }
 
@@ -650,9 +786,9 @@ template <bool K16>
 __device__ __forceinline__ void chain_release(Chain<K16>& k, int pos) {
   while (((k.released + 1) << kCFShift) <= pos) {
     __syncwarp();  // every lane is done reading the chunk
-    if (k.lane == 0) mbar_arrive(k.wempty + k.eslot);
+    if (k.lane == 0) mbar_arrive(k.wempty() + k.eslot);
     k.released++;
-    if (++k.eslot == k.nsw) k.eslot = 0;
+    if (++k.eslot == k.nsw()) k.eslot = 0;
   }
 }
 
@@ -661,12 +797,12 @@ __device__ __forceinline__ void chain_post(Chain<K16>& k, int kind, int pos, int
   TS_BEGIN();
   if (k.nposted - k.known_done >= kQ) {
     do {
-      k.known_done = ld_volatile_s32(k.ctrl);
+      k.known_done = ld_volatile_s32(k.ctrl());
     } while (k.nposted - k.known_done >= kQ);
   }
   if (k.lane == 0) {
-    k.recs[k.qslot] = make_int4(pos, period | (kind << 16), n, opos);
-    mbar_arrive(k.qfull + k.qslot);  // release: the record is visible to whoever sees the arrival
+    k.recs()[k.qslot] = make_int4(pos, period | (kind << 16), n, opos);
+    mbar_arrive(k.qfull() + k.qslot);  // release: the record is visible to whoever sees the arrival
   }
   k.nposted++;
   if (++k.qslot == kQ) k.qslot = 0;
@@ -674,22 +810,20 @@ __device__ __forceinline__ void chain_post(Chain<K16>& k, int kind, int pos, int
 }
 
 template <bool K16>
-__device__ void chain_role(const K4Params& p, const SpliceLayout& L, unsigned char* smem, int s, const Plan& pl) {
+__device__ void chain_role(const K4Params& p, const SpliceLayout& L, int s, const Plan& pl) {
   const Geometry& g = p.g;
   Chain<K16> k;
   k.lane = threadIdx.x & 31;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
-  k.wfull = bars + 2 * L.nsr;
-  k.wempty = k.wfull + L.nsw;
-  k.qfull = k.wempty + L.nsw;
-  k.ctrl = reinterpret_cast<int*>(smem + L.ctrl);
-  k.recs = reinterpret_cast<int4*>(smem + L.recs);
-  float* rcp = reinterpret_cast<float*>(smem + L.rcp);
-  k.rcp = rcp;
-  k.ds = reinterpret_cast<int*>(smem + L.ds);
-  k.win = reinterpret_cast<int*>(smem + L.win);
-  k.rw = L.rw;
-  k.nsw = L.nsw;
+  k.o_win = L.win;
+  k.o_ds = L.ds;
+  k.o_rcp = L.rcp;
+  k.o_recs = L.recs;
+  k.o_ctrl = L.ctrl;
+  k.o_wempty = L.bars + (2 * L.nsr + L.nsw) * 8;
+  k.o_qfull = L.bars + (2 * L.nsr + 2 * L.nsw) * 8;
+  k.rw_ = L.rw;
+  k.nsw_ = L.nsw;
+  float* rcp = k.rcp();
   k.S = g.step;
   k.minP = g.min_period;
   k.maxP = g.max_period;
@@ -701,7 +835,10 @@ __device__ void chain_role(const K4Params& p, const SpliceLayout& L, unsigned ch
   k.ds_count = k.maxReq / k.skip;
   // reciprocals of the lags (the float keys of the arg-min), the decimated copy's pad
   for (int n = k.lane; n < ((k.maxP + 8) & ~3); n += 32) rcp[n] = n ? __frcp_rn((float)n) : 0.f;
-  for (int i = k.lane; i < 32; i += 32) k.ds[k.maxReq / k.skip + i] = 0;
+  for (int i = k.lane; i < 32; i += 32) k.ds()[k.maxReq / k.skip + i] = 0;
+  if (K16) {
+    for (int i = k.lane; i < 7 * 64; i += 32) k.part()[i] = 0u;
+  }
   {
     unsigned m = p.lane_map[k.lane];
     // (opaque: kept in a register, not re-read from the parameter bank with a per-lane index
@@ -800,7 +937,7 @@ __device__ void chain_role(const K4Params& p, const SpliceLayout& L, unsigned ch
           if (outCount + n > cap) { status |= 1; outCount = cap; } else { outCount += n; }
           pos += n;
           woff += n;
-          if (woff >= k.rw) woff -= k.rw;
+          if (woff >= k.rw()) woff -= k.rw();
           chain_release(k, pos);
         }
       }
@@ -858,7 +995,7 @@ __device__ void chain_role(const K4Params& p, const SpliceLayout& L, unsigned ch
     }
     pos += adv;
     woff += adv;
-    if (woff >= k.rw) woff -= k.rw;
+    if (woff >= k.rw()) woff -= k.rw();
     chain_release(k, pos);
   }
 
@@ -885,7 +1022,7 @@ __device__ void chain_role(const K4Params& p, const SpliceLayout& L, unsigned ch
 #endif
   chain_post(k, REC_EXIT, pos, 0, 0, outCount);
   if (k.lane == 0) {
-    st_volatile_s32(k.ctrl + 1, 1);  // the filler stops waiting for window slots
+    st_volatile_s32(k.ctrl() + 1, 1);  // the filler stops waiting for window slots
     p.st.sonic_head[s] = head;
     p.st.sonic_fed[s] = fed;
     p.st.out_total[s] = outTotal;
@@ -902,26 +1039,27 @@ __device__ void chain_role(const K4Params& p, const SpliceLayout& L, unsigned ch
 // filler role
 // ---------------------------------------------------------------------------
 // wait on `bar` unless the chain has finished (it then never frees another slot)
-__device__ __forceinline__ bool wait_or_done(uint64_t* bar, unsigned parity, const int* done_flag) {
-  while (!mbar_try_wait_sleep(bar, parity, 2000u)) {
+__device__ __forceinline__ bool wait_or_done(uint64_t* bar, unsigned parity, const int* done_flag, unsigned poll_ns) {
+  while (!mbar_try_wait_sleep(bar, parity, poll_ns)) {
     if (ld_volatile_s32(done_flag)) return false;
-    __nanosleep(1000);
+    __nanosleep(poll_ns);
   }
   return true;
 }
 
 
-__device__ void filler_role(const K4Params& p, const SpliceLayout& L, unsigned char* smem, const Plan& pl) {
+__device__ void filler_role(const K4Params& p, const SpliceLayout& L, const Plan& pl) {
   const int lane = threadIdx.x & 31;
   const int C = p.g.channels;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(splice_smem + L.bars);
   uint64_t* rfull = bars;
   uint64_t* rempty = bars + L.nsr;
   uint64_t* wfull = bars + 2 * L.nsr;
   uint64_t* wempty = wfull + L.nsw;
-  const int* done_flag = reinterpret_cast<const int*>(smem + L.ctrl) + 1;
-  int* win = reinterpret_cast<int*>(smem + L.win);
-  short* raw = reinterpret_cast<short*>(smem + L.raw);
+  int* ctrl = reinterpret_cast<int*>(splice_smem + L.ctrl);
+  const int* done_flag = ctrl + 1;
+  int* win = reinterpret_cast<int*>(splice_smem + L.win);
+  short* raw = reinterpret_cast<short*>(splice_smem + L.raw);
   const unsigned chunk_bytes = (unsigned)(kCF * C * sizeof(short));
   const long long lim = pl.base + pl.data_end;  // absolute frames >= lim read as silence
 
@@ -938,7 +1076,7 @@ __device__ void filler_role(const K4Params& p, const SpliceLayout& L, unsigned c
         // (never sit on a landed chunk waiting for room to prefetch)
         if (issued > c) {
           if (!mbar_test(rempty + islot, (iuse - 1) & 1)) break;
-        } else if (!wait_or_done(rempty + islot, (iuse - 1) & 1, done_flag)) {
+        } else if (!wait_or_done(rempty + islot, (iuse - 1) & 1, done_flag, L.poll_ns)) {
           live = false;
           break;
         }
@@ -978,7 +1116,7 @@ __device__ void filler_role(const K4Params& p, const SpliceLayout& L, unsigned c
     }
     if (!live) break;
     const int wslot = c % L.nsw, wuse = c / L.nsw;
-    if (wuse >= 1 && !wait_or_done(wempty + wslot, (wuse - 1) & 1, done_flag)) break;
+    if (wuse >= 1 && !wait_or_done(wempty + wslot, (wuse - 1) & 1, done_flag, L.poll_ns)) break;
     const int rslot = c % L.nsr;
     mbar_wait_sleep(rfull + rslot, (c / L.nsr) & 1);
     widened = c + 1;
@@ -1006,7 +1144,11 @@ __device__ void filler_role(const K4Params& p, const SpliceLayout& L, unsigned c
         if (wslot * kCF + f < L.mir) wd[L.rw + f] = v;
       }
     }
-    mbar_arrive(wfull + wslot);  // all 32 lanes: each one's stores are released by its own arrival
+    __syncwarp();
+    if (lane == 0) {
+      __threadfence_block();  // the chunk is in the window before the count says so
+      st_volatile_s32(ctrl + 2, c + 1);
+    }
   }
   // no bulk copy may still be in flight when the CTA retires
   for (int c = widened; c < issued; c++) mbar_wait(rfull + c % L.nsr, (c / L.nsr) & 1);
@@ -1063,7 +1205,7 @@ __device__ __forceinline__ void out_overlap_add(const Output& o, int rd, int ru,
   }
 }
 
-__device__ void output_role(const K4Params& p, const SpliceLayout& L, unsigned char* smem, int s, const Plan& pl) {
+__device__ void output_role(const K4Params& p, const SpliceLayout& L, int s, const Plan& pl) {
   const Geometry& g = p.g;
   Output o;
   o.lane = threadIdx.x & 31;
@@ -1071,17 +1213,17 @@ __device__ void output_role(const K4Params& p, const SpliceLayout& L, unsigned c
   o.rrC = L.rr * g.channels;
   o.omask = L.or_elems - 1;
   o.maxP = g.max_period;
-  o.raw = reinterpret_cast<const short*>(smem + L.raw);
-  o.oring = reinterpret_cast<short*>(smem + L.oring);
-  unsigned* magic_tab = reinterpret_cast<unsigned*>(smem + L.magic);
+  o.raw = reinterpret_cast<const short*>(splice_smem + L.raw);
+  o.oring = reinterpret_cast<short*>(splice_smem + L.oring);
+  unsigned* magic_tab = reinterpret_cast<unsigned*>(splice_smem + L.magic);
   o.magic_tab = magic_tab;
   o.out = p.out + (size_t)s * p.out_capacity * g.channels;
   o.cap_e = p.out_capacity * g.channels;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(splice_smem + L.bars);
   uint64_t* rempty = bars + L.nsr;
   uint64_t* qfull = bars + 2 * L.nsr + 2 * L.nsw;
-  const int4* recs = reinterpret_cast<const int4*>(smem + L.recs);
-  int* ctrl = reinterpret_cast<int*>(smem + L.ctrl);
+  const int4* recs = reinterpret_cast<const int4*>(splice_smem + L.recs);
+  int* ctrl = reinterpret_cast<int*>(splice_smem + L.ctrl);
   // the overlap-add's division constants, once per launch
   for (int n = 2 + o.lane; n <= o.maxP; n += 32) magic_tab[n] = division_magic(n, 31 - __clz(n - 1));
   // output elements below `fe` are in the stream's row; [fe, ee) sit in the ring
@@ -1184,11 +1326,10 @@ __device__ void output_role(const K4Params& p, const SpliceLayout& L, unsigned c
 
 template <bool K16>
 __global__ void __launch_bounds__(kThreads, 7) k4_splice(K4Params p, SpliceLayout L) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int s = blockIdx.x;
   if (s >= p.n_streams) return;
   const int warp = threadIdx.x >> 5;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + L.bars);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(splice_smem + L.bars);
   if (threadIdx.x == 0) {
     for (int i = 0; i < L.nsr; i++) {
       mbar_init(bars + i, 1);          // rfull: the bulk copy's bytes (or the filler's plain loads)
@@ -1199,17 +1340,18 @@ __global__ void __launch_bounds__(kThreads, 7) k4_splice(K4Params p, SpliceLayou
       mbar_init(bars + 2 * L.nsr + L.nsw + i, 1);  // wempty: the chain
     }
     for (int i = 0; i < kQ; i++) mbar_init(bars + 2 * L.nsr + 2 * L.nsw + i, 1);  // qfull: the chain
-    int* ctrl = reinterpret_cast<int*>(smem_raw + L.ctrl);
-    ctrl[0] = 0;
-    ctrl[1] = 0;
+    int* ctrl = reinterpret_cast<int*>(splice_smem + L.ctrl);
+    ctrl[0] = 0;  // records the output role has finished
+    ctrl[1] = 0;  // the chain is done
+    ctrl[2] = 0;  // window chunks the filler has widened
     fence_barrier_init();
   }
   __syncthreads();
   const Plan pl = make_plan(p, s);
   __syncthreads();  // every role has read the stream's state before the chain rewrites it
-  if (warp == 0) chain_role<K16>(p, L, smem_raw, s, pl);
-  else if (warp == 1) filler_role(p, L, smem_raw, pl);
-  else output_role(p, L, smem_raw, s, pl);
+  if (warp == 0) chain_role<K16>(p, L, s, pl);
+  else if (warp == 1) filler_role(p, L, pl);
+  else output_role(p, L, s, pl);
 }
 
 // Can the pipelined shape take this launch?  (Mono streams, a fine search that fits one round
@@ -1226,49 +1368,23 @@ cudaError_t launch_k4_splice(const K4Params& p0, cudaStream_t stream) {
   K4Params p = p0;
   const Geometry& g = p.g;
   k4_lane_map(p, 1);
-  SpliceLayout L;
-  const int span = g.max_required + kPadW;  // what one search needs in the window
-  const int span_chunks = (span + kCF - 1) / kCF;
-  L.depth = 6;
-  L.nsr = span_chunks + 1 + L.depth + 1;
-  L.nsw = span_chunks + 1 + 3;
+  int depth = kDepthDefault, nsw_override = 0;
+  bool tuned = false;
   if (const char* e = getenv("SPEEDY_K4_NSW")) {
     const int v = atoi(e);
-    if (v >= span_chunks + 2 && v <= 32) L.nsw = v;
+    if (v >= (g.max_required + kPadW + kCF - 1) / kCF + 2 && v <= 32) nsw_override = v, tuned = true;
   }
   if (const char* e = getenv("SPEEDY_K4_DEPTH")) {
     const int d = atoi(e);
-    if (d >= 1 && d <= 16) {
-      L.depth = d;
-      L.nsr = span_chunks + 1 + L.depth + 1;
-    }
+    if (d >= 1 && d <= 16) depth = d, tuned = true;
   }
-  L.rw = L.nsw * kCF;
-  L.rr = L.nsr * kCF;
-  L.mir = (span + 15) & ~15;
-  int or_elems = 1024;
-  while (or_elems < g.max_required * g.channels + 64) or_elems <<= 1;
-  L.or_elems = or_elems;
+  SpliceLayout L = make_layout(g.max_period, g.max_required, g.skip, g.channels, depth, nsw_override);
+  if (const char* e = getenv("SPEEDY_K4_POLL_NS")) L.poll_ns = atoi(e) > 0 ? atoi(e) : 500;
   L.out_vec = ((p.out_capacity * g.channels) % 8 == 0 && (reinterpret_cast<size_t>(p.out) & 15) == 0) ? 1 : 0;
-  int off = 0;
-  auto take = [&off](int bytes) {
-    const int at = off;
-    off += (bytes + 15) & ~15;
-    return at;
-  };
-  L.bars = take((2 * L.nsr + 2 * L.nsw + kQ) * 8);
-  L.ctrl = take(16);
-  L.recs = take(kQ * 16);
-  L.rcp = take(((g.max_period + 8) & ~3) * 4);
-  L.magic = take(((g.max_period + 4) & ~3) * 4);
-  L.ds = take((g.max_required / g.skip + 32 + 16) * 4);
-  L.win = take((L.rw + L.mir) * 4);
-  L.raw = take(L.rr * g.channels * 2);
-  L.oring = take(L.or_elems * 2);
-  L.total = off;
   // the shared-memory opt-in is per device (and cheap): set it on every launch
   // 16 kHz streams take the instantiation with compile-time geometry
-  const bool skip4 = g.rate == 16000 && g.step == 160 && g.min_period == 40 && g.max_period == 246 && g.skip == 4;
+  const bool skip4 = !tuned && g.channels == 1 && g.rate == 16000 && g.step == 160 && g.min_period == 40 &&
+                     g.max_period == 246 && g.skip == 4;  // kLay16 is this layout
   cudaError_t e = skip4 ? cudaFuncSetAttribute(k4_splice<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total)
                         : cudaFuncSetAttribute(k4_splice<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
   if (e != cudaSuccess) return e;
