@@ -32,7 +32,7 @@ for i, nm in enumerate(names):
     table['phases'][nm] = {'cycles': int(out[i]), 'share': float(out[i]) / tot, 'per_iteration': float(out[i]) / max(it, 1)}
 other = tot - int(out[:8].sum())
 table['phases']['other'] = {'cycles': other, 'share': other / tot, 'per_iteration': other / max(it, 1)}
-table['window_chunks_waited'] = int(out[11]); table['window_chunks_not_ready'] = int(out[12])
+table['filler_waited_window_slot'] = int(out[5]); table['not_ready_chunks_short_sum'] = int(out[3]); table['not_ready_need_minus_released_sum'] = int(out[7]); table['filler_blocked_on_raw_slot'] = int(out[15]); table['window_checks'] = int(out[11]); table['window_not_ready'] = int(out[12]); table['queue_full_events'] = int(out[13]); table['mean_records_pending_at_check'] = float(out[14]) / max(int(out[11]), 1)
 print(json.dumps(table, indent=1))
 if dst:
     json.dump(table, open(dst, 'w'), indent=1)

@@ -53,6 +53,7 @@
 // registers and combine them with shuffles; no shared-memory accumulators.
 #include <stdlib.h>
 
+#include "amdf16.cuh"
 #include "kernels.cuh"
 
 namespace speedy {
@@ -76,7 +77,7 @@ constexpr int kPad = 32;  // over-read slack behind the window and the decimated
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kMaxGroups = 64;  // lag groups of four per search (>= 2 * skip + 2)
 
-template <int NW, int CH>
+template <int NW, int CH, bool K16 = false>
 struct Sonic {
   static constexpr int VL = 32 * NW;  // lanes cooperating on one stream
   // geometry
@@ -106,6 +107,11 @@ struct Sonic {
   int cGi, cSub, cG, cMaxG;
   unsigned dec_magic;
   const unsigned* magic_tab;  // ceil(2^(32+s) / n) for n = 2 .. maxP, or null (computed on demand)
+  float* rcp16;               // K16: 1 / lag table of the shared 16 kHz pitch search (amdf16.cuh)
+  __device__ __forceinline__ int* win() const { return w32; }
+  __device__ __forceinline__ int* ds() const { return ds32; }
+  __device__ __forceinline__ float* rcp() const { return rcp16; }
+  __device__ __forceinline__ unsigned* part() const { return sums; }
   bool fold_all;  // few streams per SM (latency bound): every lane runs the fold rather than branching around it
   bool timing;
 
@@ -507,6 +513,7 @@ struct Sonic {
 
   __device__ __forceinline__ int find_pitch_period(long long pos) {
     const int off = (int)(pos - bufStart);
+    if (K16) return amdf16::find_pitch_period(*this, off);  // 16 kHz mono, one warp: compile-time geometry
     int minDiff = 0, maxDiff = 0, period = 0;
     const int* arr = w32;
     int aoff = off;
@@ -616,6 +623,7 @@ __host__ __device__ inline size_t k4_stream_smem(const Geometry& g, int buf_fram
   b += (size_t)((g.max_required / g.skip + kPad + 3) & ~3) * sizeof(int);
   b += (size_t)2 * 4 * kMaxGroups * sizeof(unsigned);
   b += (size_t)((g.max_period + 4) & ~3) * sizeof(unsigned);  // overlap-add division constants
+  b += (size_t)((g.max_period + 8) & ~3) * sizeof(float);     // reciprocals of the lags (16 kHz search)
   if (g.channels > 1) b += (size_t)buf_frames * g.channels * sizeof(short) + 16;  // + one vector of over-read
   return (b + 15) & ~(size_t)15;
 }
@@ -625,14 +633,14 @@ __host__ __device__ inline size_t k4_stream_smem(const Geometry& g, int buf_fram
 // MINB: resident CTAs per SM the register allocation is held to (1 = unconstrained).
 // Few streams: registers are free, latency is what counts.  Many streams: 16 resident
 // warps per SM hide the chain's latency, worth a tighter allocation.
-template <int NW, int MINB, int CH, bool HOSTMAP>
+template <int NW, int MINB, int CH, bool HOSTMAP, bool K16 = false>
 __global__ void __launch_bounds__(NW * 32, MINB) k4_sonic(K4Params p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int s = blockIdx.x;
   if (s >= p.n_streams) return;
   const Geometry& g = p.g;
 
-  Sonic<NW, CH> k;
+  Sonic<NW, CH, K16> k;
   k.lane = threadIdx.x & 31;
   k.warp = threadIdx.x >> 5;
   k.vl = threadIdx.x;
@@ -656,7 +664,12 @@ __global__ void __launch_bounds__(NW * 32, MINB) k4_sonic(K4Params p) {
   k.ds32 = k.w32 + k.bufN + kPad;
   k.sums = reinterpret_cast<unsigned*>(k.ds32 + ((k.maxReq / k.skip + kPad + 3) & ~3));
   unsigned* magic_tab = k.sums + 2 * 4 * kMaxGroups;  // [(maxP + 4) & ~3]
-  k.buf = reinterpret_cast<short*>(magic_tab + ((k.maxP + 4) & ~3));
+  k.rcp16 = reinterpret_cast<float*>(magic_tab + ((k.maxP + 4) & ~3));
+  k.buf = reinterpret_cast<short*>(k.rcp16 + ((k.maxP + 8) & ~3));
+  if (K16) {
+    for (int n = k.vl; n < ((k.maxP + 8) & ~3); n += Sonic<NW, CH>::VL) k.rcp16[n] = n ? __frcp_rn((float)n) : 0.f;
+    for (int n = k.vl; n < 2 * 4 * kMaxGroups; n += Sonic<NW, CH>::VL) k.sums[n] = 0u;  // rows no lane writes stay zero
+  }
   // long launches: the overlap-add's division constants once, off the splice chain (a
   // double division per pitch iteration otherwise); short ones compute the few they need
   k.magic_tab = HOSTMAP ? nullptr : magic_tab;
@@ -929,19 +942,21 @@ static int k4_buf_frames(const Geometry& g, int n_streams) {
   return n & ~63;
 }
 
-template <int NW, int MINB, int CH, bool HOSTMAP>
+template <int NW, int MINB, int CH, bool HOSTMAP, bool K16 = false>
 static cudaError_t launch_k4_c(K4Params& p, cudaStream_t stream) {
   const size_t smem = k4_stream_smem(p.g, p.buf_frames);
-  static size_t attr = 0;
-  if (smem > attr) {
-    cudaError_t e = cudaFuncSetAttribute(k4_sonic<NW, MINB, CH, HOSTMAP>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    attr = smem;
-  }
-  k4_sonic<NW, MINB, CH, HOSTMAP><<<p.n_streams, NW * 32, smem, stream>>>(p);
+  // the shared-memory opt-in is per device (and cheap): set on every launch
+  cudaError_t e = cudaFuncSetAttribute(k4_sonic<NW, MINB, CH, HOSTMAP, K16>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k4_sonic<NW, MINB, CH, HOSTMAP, K16><<<p.n_streams, NW * 32, smem, stream>>>(p);
   count_launch();
   return cudaGetLastError();
+}
+
+// 16 kHz mono: the pitch search with compile-time geometry (amdf16.cuh)
+static bool k4_is_16k_mono(const Geometry& g) {
+  return g.channels == 1 && g.rate == 16000 && g.step == 160 && g.min_period == 40 && g.max_period == 246 && g.skip == 4;
 }
 
 template <int NW, int MINB>
@@ -950,8 +965,10 @@ static cudaError_t launch_k4_t(K4Params& p, cudaStream_t stream) {
   const bool short_launch = p.flush || p.frames - p.done <= p.g.rate;
   if (short_launch) {
     k4_lane_map(p, NW);
+    if (NW == 1 && k4_is_16k_mono(p.g)) return launch_k4_c<NW, MINB, 1, true, NW == 1>(p, stream);
     return p.g.channels == 1 ? launch_k4_c<NW, MINB, 1, true>(p, stream) : launch_k4_c<NW, MINB, 0, true>(p, stream);
   }
+  if (NW == 1 && k4_is_16k_mono(p.g)) return launch_k4_c<NW, MINB, 1, false, NW == 1>(p, stream);
   return p.g.channels == 1 ? launch_k4_c<NW, MINB, 1, false>(p, stream) : launch_k4_c<NW, MINB, 0, false>(p, stream);
 }
 

@@ -32,6 +32,7 @@
 // of the one-warp kernel is gone.
 #include <stdlib.h>
 
+#include "amdf16.cuh"
 #include "kernels.cuh"
 
 namespace speedy {
@@ -49,10 +50,10 @@ __device__ unsigned long long g_k4s_cycles[16];
 
 namespace {
 
-constexpr unsigned kFull = 0xffffffffu;
+using amdf16::kFull;
 constexpr int kCF = 256;     // frames per ring chunk
 constexpr int kCFShift = 8;
-constexpr int kQ = 8;        // splice records in flight
+constexpr int kQ = 16;       // splice records in flight
 constexpr int kPadW = 16;    // frames the AMDF may read past a search span
 constexpr int kThreads = 96;
 
@@ -88,7 +89,7 @@ __host__ __device__ constexpr SpliceLayout make_layout(int max_period, int max_r
   const int span = max_required + kPadW;  // what one search needs in the window
   const int span_chunks = (span + kCF - 1) / kCF;
   L.depth = depth;
-  L.nsr = span_chunks + 1 + depth + 1;
+  L.nsr = span_chunks + 1 + depth + 1 + 6;  // (+ what the records still queued for the output role hold)
   L.nsw = nsw_override > 0 ? nsw_override : span_chunks + 1 + kWindowAhead;
   L.rw = L.nsw * kCF;
   L.rr = L.nsr * kCF;
@@ -176,7 +177,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
   }
 }
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, unsigned parity) {
+#ifdef K4_NOSLEEP
+  while (!mbar_try_wait(bar, parity)) {
+  }
+#else
   while (!mbar_try_wait_sleep(bar, parity, 2000u)) __nanosleep(500);
+#endif
 }
 // global -> shared bulk copy (TMA, 1-D), completion counted in bytes on `bar`
 __device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
@@ -338,91 +344,10 @@ struct Chain {
   __device__ __forceinline__ int gCHi() const { return K16 ? 61 : c_hi; }
 };
 
-// The 16 |a - b| terms of one aligned block of four samples for the four lags pg .. pg+3
-// (pg a multiple of four), every sample valid for every lag.
-__device__ __forceinline__ void sad16(const int4& av, const int4& b0, const int4& b1, unsigned (&d)[4]) {
-  d[0] = __sad(av.x, b0.x, d[0]); d[1] = __sad(av.x, b0.y, d[1]);
-  d[2] = __sad(av.x, b0.z, d[2]); d[3] = __sad(av.x, b0.w, d[3]);
-  d[0] = __sad(av.y, b0.y, d[0]); d[1] = __sad(av.y, b0.z, d[1]);
-  d[2] = __sad(av.y, b0.w, d[2]); d[3] = __sad(av.y, b1.x, d[3]);
-  d[0] = __sad(av.z, b0.z, d[0]); d[1] = __sad(av.z, b0.w, d[1]);
-  d[2] = __sad(av.z, b1.x, d[2]); d[3] = __sad(av.z, b1.y, d[3]);
-  d[0] = __sad(av.w, b0.w, d[0]); d[1] = __sad(av.w, b1.x, d[1]);
-  d[2] = __sad(av.w, b1.y, d[2]); d[3] = __sad(av.w, b1.z, d[3]);
-}
-
-#define LD4(p) (*reinterpret_cast<const int4*>(p))
-
-// Fully valid blocks j, j + step, ... < jend of one lag group (3 LDS.128 + 16 VABSDIFF each).
-// Two register sets in turn: the loads of the next block are in flight while this one's
-// differences issue (a lone warp has nobody to hide the shared-memory latency behind).
-__device__ __forceinline__ void blocks_run(const int* base, int pg, int j, int step, int jend, unsigned (&d)[4]) {
-  if (j >= jend) return;
-  const int* pa = base + 4 * j;
-  const int stride = 4 * step;
-  int4 a0 = LD4(pa), b00 = LD4(pa + pg), b01 = LD4(pa + pg + 4);
-  int4 a1, b10, b11;
-#pragma unroll 1
-  for (;;) {
-    j += step;
-    if (j >= jend) {
-      sad16(a0, b00, b01, d);
-      break;
-    }
-    pa += stride;
-    a1 = LD4(pa); b10 = LD4(pa + pg); b11 = LD4(pa + pg + 4);
-    sad16(a0, b00, b01, d);
-    j += step;
-    if (j >= jend) {
-      sad16(a1, b10, b11, d);
-      break;
-    }
-    pa += stride;
-    a0 = LD4(pa); b00 = LD4(pa + pg); b01 = LD4(pa + pg + 4);
-    sad16(a1, b10, b11, d);
-  }
-}
-
-// The ragged start of a lag group's range: the block that holds the first sample when the
-// range does not start on a block boundary (hd = 1 .. 3 samples in): sample m counts for
-// every lag iff m >= hd.
-__device__ __forceinline__ void block_head(const int* base, int pg, int hd, unsigned (&d)[4]) {
-  const int4 a = LD4(base), b0 = LD4(base + pg), b1 = LD4(base + pg + 4);
-  d[0] = __sad(a.w, b0.w, d[0]); d[1] = __sad(a.w, b1.x, d[1]);
-  d[2] = __sad(a.w, b1.y, d[2]); d[3] = __sad(a.w, b1.z, d[3]);
-  if (hd <= 2) {
-    d[0] = __sad(a.z, b0.z, d[0]); d[1] = __sad(a.z, b0.w, d[1]);
-    d[2] = __sad(a.z, b1.x, d[2]); d[3] = __sad(a.z, b1.y, d[3]);
-  }
-  if (hd <= 1) {
-    d[0] = __sad(a.y, b0.y, d[0]); d[1] = __sad(a.y, b0.z, d[1]);
-    d[2] = __sad(a.y, b0.w, d[2]); d[3] = __sad(a.y, b1.x, d[3]);
-  }
-}
-
-// The ragged end: `pa` is the first block that is not fully valid for all four lags.  Its
-// sample m counts for lag pg + l iff m < c + l, c = hd (pg is a multiple of four): the c
-// samples every lag still has, then l more for lag pg + l.  Six terms are unconditional
-// (m < l), the other twelve hang off three predicates.
-__device__ __forceinline__ void block_tail(const int* pa, int pg, int c, unsigned (&d)[4]) {
-  const int4 a0 = LD4(pa), a1 = LD4(pa + 4);
-  const int4 b0 = LD4(pa + pg), b1 = LD4(pa + pg + 4), b2 = LD4(pa + pg + 8);
-  d[1] = __sad(a0.x, b0.y, d[1]);
-  d[2] = __sad(a0.x, b0.z, d[2]); d[2] = __sad(a0.y, b0.w, d[2]);
-  d[3] = __sad(a0.x, b0.w, d[3]); d[3] = __sad(a0.y, b1.x, d[3]); d[3] = __sad(a0.z, b1.y, d[3]);
-  if (c > 0) {
-    d[0] = __sad(a0.x, b0.x, d[0]); d[1] = __sad(a0.y, b0.z, d[1]);
-    d[2] = __sad(a0.z, b1.x, d[2]); d[3] = __sad(a0.w, b1.z, d[3]);
-  }
-  if (c > 1) {
-    d[0] = __sad(a0.y, b0.y, d[0]); d[1] = __sad(a0.z, b0.w, d[1]);
-    d[2] = __sad(a0.w, b1.y, d[2]); d[3] = __sad(a1.x, b1.w, d[3]);
-  }
-  if (c > 2) {
-    d[0] = __sad(a0.z, b0.z, d[0]); d[1] = __sad(a0.w, b1.x, d[1]);
-    d[2] = __sad(a1.x, b1.z, d[2]); d[3] = __sad(a1.y, b2.x, d[3]);
-  }
-}
+using amdf16::sad16;
+using amdf16::blocks_run;
+using amdf16::block_head;
+using amdf16::block_tail;
 
 // Exact resolution of a short list of candidates, in the order of the C scan
 // (oracle/sonic_oracle.c:189-205): lanes ascend with the lag, so does l.  Rare (several
@@ -456,39 +381,7 @@ __device__ __noinline__ void resolve_exact(unsigned d0, unsigned d1, unsigned d2
   *rp = bp;
 }
 
-// The same for the one-lag-per-lane form: lane i holds the sums of lags base + i (sa) and
-// base + 32 + i (sb); candidates are ballots.
-__device__ __noinline__ void resolve_exact2(unsigned sa, unsigned sb, unsigned bal_a, unsigned bal_b, int base,
-                                            int want_min, unsigned* rd, int* rp) {
-  unsigned bd = 0u;
-  int bp = want_min ? 0 : 255;
-#pragma unroll 1
-  for (int half = 0; half < 2; half++) {
-    unsigned bal = half ? bal_b : bal_a;
-    while (bal) {
-      const int src = __ffs(bal) - 1;
-      bal &= bal - 1;
-      const unsigned cd = __shfl_sync(kFull, half ? sb : sa, src);
-      const int cp = base + 32 * half + src;
-      const unsigned long long lhs = (unsigned long long)cd * (unsigned)bp;
-      const unsigned long long rhs = (unsigned long long)bd * (unsigned)cp;
-      if (want_min ? (bp == 0 || lhs < rhs) : (lhs > rhs)) {
-        bd = cd;
-        bp = cp;
-      }
-    }
-  }
-  *rd = bd;
-  *rp = bp;
-}
-
-// floor(a / b) for a < 2^27, 0 < b < 2^11 (quotient < 2^16) from the float reciprocal of b:
-// the estimate is off by at most one either way, one fix-up per side.
-__device__ __forceinline__ int udiv_small(unsigned a, int b, float rcp_b) {
-  const int q = (int)(__uint2float_rn(a) * rcp_b);
-  const int rem = (int)a - q * b;
-  return q + (rem >= b ? 1 : 0) - (rem < 0 ? 1 : 0);
-}
+using amdf16::udiv_small;
 
 // AMDF over lags lo..hi on a[i] = arr[off + i] (oracle/sonic_oracle.c:185-209): lane
 // `sub` of the `G` adjacent lanes of a lag group (lags pg .. pg+3, pg a multiple of four)
@@ -518,62 +411,6 @@ __device__ __forceinline__ int search(const Chain<K16>& k, const int* arr, int o
     blocks_run(base, pg, (hd ? 1 : 0) + sub, G, jf1, d);
     if (sub == 0 && hd) block_head(base, pg, hd, d);
     if (sub == (G > 1 ? 1 : 0)) block_tail(base + 4 * jf1, pg, hd, d);
-  }
-  if (K16) {
-    // 16 kHz: the partial sums go through shared memory, one row per lane of a group, and come
-    // back one lag per lane (lag base + lane, and base + 32 + lane): no shuffle tree, no
-    // four-lags-per-leader selects.  Rows a group has no lane for stay zero (coarse pass: the
-    // lane assignment is static); lags outside [lo, hi] are masked below.
-    constexpr int ROWS = MAXG;
-    unsigned* part = k.part() + (WANT_DIFFS ? 4 * 64 : 0);
-    const int base = lo & ~3;
-    if (live) *reinterpret_cast<uint4*>(part + sub * 64 + (pg - base)) = make_uint4(d[0], d[1], d[2], d[3]);
-    __syncwarp();
-    unsigned sa = 0u, sb = 0u;
-#pragma unroll
-    for (int r = 0; r < ROWS; r++) {
-      sa += part[r * 64 + k.lane];
-      sb += part[r * 64 + 32 + k.lane];
-    }
-    __syncwarp();  // (the next search of this kind rewrites the rows)
-    const int la = base + k.lane, lb = la + 32;
-    const bool va = la >= lo && la <= hi, vb = lb <= hi;
-    const float ka = __uint2float_rn(sa) * k.rcp()[va ? la : 0], kb = __uint2float_rn(sb) * k.rcp()[vb ? lb : 0];
-    const float big = 3.0e38f;
-    const float emin = __uint_as_float(__reduce_min_sync(kFull, __float_as_uint(fminf(va ? ka : big, vb ? kb : big))));
-    const float tmin = emin * 1.000002f;
-    const unsigned bal_a = __ballot_sync(kFull, va && ka <= tmin), bal_b = __ballot_sync(kFull, vb && kb <= tmin);
-    unsigned wal_a = 0u, wal_b = 0u;
-    float emax = 1.0f;
-    if (WANT_DIFFS) {
-      emax = __uint_as_float(__reduce_max_sync(kFull, __float_as_uint(fmaxf(va ? ka : 0.f, vb ? kb : 0.f))));
-      const float tmax = emax * 0.999998f;
-      wal_a = __ballot_sync(kFull, va && ka >= tmax);
-      wal_b = __ballot_sync(kFull, vb && kb >= tmax);
-    }
-    unsigned best_diff, worst_diff = 0u;
-    int best, worst = 255;
-    const bool one_min = __popc(bal_a) + __popc(bal_b) == 1;
-    const bool one_max = !WANT_DIFFS || (__popc(wal_a) + __popc(wal_b) == 1 && emax > 0.f);
-    if (one_min && one_max) {
-      const int src = __ffs(bal_a | bal_b) - 1;
-      best = base + src + (bal_a ? 0 : 32);
-      best_diff = __shfl_sync(kFull, bal_a ? sa : sb, src);
-      if (WANT_DIFFS) {
-        const int srw = __ffs(wal_a | wal_b) - 1;
-        worst = base + srw + (wal_a ? 0 : 32);
-        worst_diff = __shfl_sync(kFull, wal_a ? sa : sb, srw);
-      }
-    } else {
-      resolve_exact2(sa, sb, bal_a, bal_b, base, 1, &best_diff, &best);
-      if (WANT_DIFFS) resolve_exact2(sa, sb, wal_a, wal_b, base, 0, &worst_diff, &worst);
-    }
-    if (WANT_DIFFS) {
-      const int md = udiv_small(best_diff, best, k.rcp()[best]);
-      *minDiff = md;
-      *maxDiff = worst_diff >= (unsigned)(3 * md + 1) * (unsigned)worst ? 3 * md + 1 : 0;
-    }
-    return best;
   }
   // the group's first lane collects its neighbours' partial sums (independent shuffles)
   {
@@ -663,32 +500,7 @@ template <bool K16>
 __device__ __forceinline__ void decimate(const Chain<K16>& k, int off) {
   TS_BEGIN();
   __syncwarp();  // every lane is done reading the previous decimated copy
-  if (K16) {
-    const int r = off & 3;
-    const int4* p = reinterpret_cast<const int4*>(k.win() + (off & ~3) + 16 * k.lane);
-    const int4 x0 = p[0], x1 = p[1], x2 = p[2], x3 = p[3], x4 = p[4];
-    int s0, s1, s2, s3;
-    if (r == 0) {
-      s0 = (x0.x + x0.y) + (x0.z + x0.w); s1 = (x1.x + x1.y) + (x1.z + x1.w);
-      s2 = (x2.x + x2.y) + (x2.z + x2.w); s3 = (x3.x + x3.y) + (x3.z + x3.w);
-    } else if (r == 1) {
-      s0 = (x0.y + x0.z) + (x0.w + x1.x); s1 = (x1.y + x1.z) + (x1.w + x2.x);
-      s2 = (x2.y + x2.z) + (x2.w + x3.x); s3 = (x3.y + x3.z) + (x3.w + x4.x);
-    } else if (r == 2) {
-      s0 = (x0.z + x0.w) + (x1.x + x1.y); s1 = (x1.z + x1.w) + (x2.x + x2.y);
-      s2 = (x2.z + x2.w) + (x3.x + x3.y); s3 = (x3.z + x3.w) + (x4.x + x4.y);
-    } else {
-      s0 = (x0.w + x1.x) + (x1.y + x1.z); s1 = (x1.w + x2.x) + (x2.y + x2.z);
-      s2 = (x2.w + x3.x) + (x3.y + x3.z); s3 = (x3.w + x4.x) + (x4.y + x4.z);
-    }
-    int4 o;
-    o.x = (s0 + ((s0 >> 31) & 3)) >> 2;
-    o.y = (s1 + ((s1 >> 31) & 3)) >> 2;
-    o.z = (s2 + ((s2 >> 31) & 3)) >> 2;
-    o.w = (s3 + ((s3 >> 31) & 3)) >> 2;
-    // 128 values: the few past maxRequired / 4 only ever meet masked samples
-    reinterpret_cast<int4*>(k.ds())[k.lane] = o;
-  } else if ((k.skip & 3) == 0) {
+  if ((k.skip & 3) == 0) {
     // aligned 16-byte walk: the first and last vector of a value are partial
     const int count = k.ds_count;
     const int r = off & 3;
@@ -729,14 +541,14 @@ __device__ __forceinline__ void decimate(const Chain<K16>& k, int off) {
 // has q + 1 blocks), then the refinement at the full rate.
 template <bool K16>
 __device__ __forceinline__ int find_pitch_period(Chain<K16>& k, int off) {
+  if (K16) return amdf16::find_pitch_period(k, off);
   int minDiff = 0, maxDiff = 0, period = 0;
   int lo = k.gMinP(), hi = k.gMaxP();
   if (k.gSkip() != 1) {
     decimate<K16>(k, off);
     TS_BEGIN();
     const int cpg = 4 * ((k.gCLo() >> 2) + k.cGi);
-    if (K16) period = search<K16, 4, false, false>(k, k.ds(), 0, 10, 61, cpg, k.cGi >= 0, k.cSub, k.cG, 4, nullptr, nullptr);
-    else period = search<K16, 0, false, false>(k, k.ds(), 0, k.c_lo, k.c_hi, cpg, k.cGi >= 0, k.cSub, k.cG, k.cMaxG, nullptr, nullptr);
+    period = search<K16, 0, false, false>(k, k.ds(), 0, k.c_lo, k.c_hi, cpg, k.cGi >= 0, k.cSub, k.cG, k.cMaxG, nullptr, nullptr);
 #ifdef K4_TIMING
     if (k.lane == 0 && k.timing) atomicAdd(&g_k4s_cycles[2], (unsigned long long)(clock64() - _t0 + (period & 0)));
 #endif
@@ -752,8 +564,7 @@ __device__ __forceinline__ int find_pitch_period(Chain<K16>& k, int off) {
     const int g0 = lo >> 2;
     const int pg = 4 * (g0 + k.fGi0);
     const bool live = k.fGi0 < (hi >> 2) - g0 + 1;
-    if (K16) period = search<K16, 3, true, true>(k, k.win(), off, lo, hi, pg, live, k.fg, 3, 3, &minDiff, &maxDiff);
-    else period = search<K16, 0, false, true>(k, k.win(), off, lo, hi, pg, live, k.fg, k.fG, k.fG, &minDiff, &maxDiff);
+    period = search<K16, 0, false, true>(k, k.win(), off, lo, hi, pg, live, k.fg, k.fG, k.fG, &minDiff, &maxDiff);
 #ifdef K4_TIMING
     if (k.lane == 0 && k.timing) atomicAdd(&g_k4s_cycles[4], (unsigned long long)(clock64() - _t0 + (period & 0)));
 #endif
@@ -775,6 +586,19 @@ __device__ __forceinline__ void chain_ensure(Chain<K16>& k, int need_end) {
   const int cneed = (need_end - 1) >> kCFShift;
   if (k.cready > cneed) return;
   TS_BEGIN();
+#ifdef K4_TIMING
+  if (k.lane == 0 && k.timing) {
+    atomicAdd(&g_k4s_cycles[11], 1ULL);
+    const int have = ld_volatile_s32(k.ctrl() + 2);
+    if (have <= cneed) {
+      atomicAdd(&g_k4s_cycles[12], 1ULL);
+      atomicAdd(&g_k4s_cycles[3], (unsigned long long)(cneed + 1 - have));           // chunks short
+      atomicAdd(&g_k4s_cycles[7], (unsigned long long)(cneed - k.released));         // need - released
+    }
+    // how far behind is the output role
+    atomicAdd(&g_k4s_cycles[14], (unsigned long long)(k.nposted - ld_volatile_s32(k.ctrl())));
+  }
+#endif
   do {
     k.cready = ld_volatile_s32(k.ctrl() + 2);
   } while (k.cready <= cneed);
@@ -796,6 +620,9 @@ template <bool K16>
 __device__ __forceinline__ void chain_post(Chain<K16>& k, int kind, int pos, int period, int n, int opos) {
   TS_BEGIN();
   if (k.nposted - k.known_done >= kQ) {
+#ifdef K4_TIMING
+    if (k.lane == 0 && k.timing) atomicAdd(&g_k4s_cycles[13], 1ULL);
+#endif
     do {
       k.known_done = ld_volatile_s32(k.ctrl());
     } while (k.nposted - k.known_done >= kQ);
@@ -1040,10 +867,16 @@ __device__ void chain_role(const K4Params& p, const SpliceLayout& L, int s, cons
 // ---------------------------------------------------------------------------
 // wait on `bar` unless the chain has finished (it then never frees another slot)
 __device__ __forceinline__ bool wait_or_done(uint64_t* bar, unsigned parity, const int* done_flag, unsigned poll_ns) {
+#ifdef K4_NOSLEEP
+  while (!mbar_try_wait(bar, parity)) {
+    if (ld_volatile_s32(done_flag)) return false;
+  }
+#else
   while (!mbar_try_wait_sleep(bar, parity, poll_ns)) {
     if (ld_volatile_s32(done_flag)) return false;
     __nanosleep(poll_ns);
   }
+#endif
   return true;
 }
 
@@ -1076,7 +909,11 @@ __device__ void filler_role(const K4Params& p, const SpliceLayout& L, const Plan
         // (never sit on a landed chunk waiting for room to prefetch)
         if (issued > c) {
           if (!mbar_test(rempty + islot, (iuse - 1) & 1)) break;
-        } else if (!wait_or_done(rempty + islot, (iuse - 1) & 1, done_flag, L.poll_ns)) {
+        } else if (
+#ifdef K4_TIMING
+            (blockIdx.x == 0 && lane == 0 && !mbar_test(rempty + islot, (iuse - 1) & 1) ? (void)atomicAdd(&g_k4s_cycles[15], 1ULL) : (void)0),
+#endif
+            !wait_or_done(rempty + islot, (iuse - 1) & 1, done_flag, L.poll_ns)) {
           live = false;
           break;
         }
@@ -1116,6 +953,11 @@ __device__ void filler_role(const K4Params& p, const SpliceLayout& L, const Plan
     }
     if (!live) break;
     const int wslot = c % L.nsw, wuse = c / L.nsw;
+#ifdef K4_TIMING
+    if (blockIdx.x == 0 && lane == 0 && wuse >= 1) {
+      if (!mbar_test(wempty + wslot, (wuse - 1) & 1)) atomicAdd(&g_k4s_cycles[5], 1ULL);
+    }
+#endif
     if (wuse >= 1 && !wait_or_done(wempty + wslot, (wuse - 1) & 1, done_flag, L.poll_ns)) break;
     const int rslot = c % L.nsr;
     mbar_wait_sleep(rfull + rslot, (c / L.nsr) & 1);
