@@ -16,7 +16,7 @@ sb.synth_device(d_in, 0, n, rate, 1, frames)
 b = sb.Batch(n, rate, 1, speed=speed, nonlinear=1.0, feedback=0.1, max_write_frames=frames, out_capacity=frames + 4096)
 import os
 L = sb.lib()
-splice = not os.environ.get('SPEEDY_K4_LEGACY')
+splice = bool(os.environ.get('SPEEDY_K4_PIPELINE'))
 dbg = L.speedyDebugK4SpliceCycles if splice else L.speedyDebugK4Cycles
 dbg.argtypes = [C.c_void_p, C.c_int]
 for it in range(2):

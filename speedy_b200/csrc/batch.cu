@@ -304,7 +304,9 @@ struct speedyBatchStruct {
   int16_t* d_out;
   long long out_capacity;
   // override speeds
-  float* d_override;
+  float* d_override;           // current rows (null: none)
+  float* d_override_buf;       // the allocation behind them, reused while it is large enough
+  size_t override_capacity;    // floats
   long long override_stride;
   // taps
   float *d_tap_spec, *d_tap_energy, *d_tap_features, *d_tap_tension, *d_tap_speed;
@@ -465,6 +467,8 @@ speedyBatch speedyBatchCreate(const speedyBatchConfig* cfg) {
   b->stage_frames = 0;
   b->d_counts_stage = nullptr;
   b->d_override = nullptr;
+  b->d_override_buf = nullptr;
+  b->override_capacity = 0;
   b->override_stride = 0;
   b->pipe_ready = 0;
   b->s_h2d = b->s_d2h = nullptr;
@@ -654,10 +658,27 @@ int speedyBatchOverrideSpeeds(speedyBatch b, const float* speeds, int64_t frames
     b->override_stride = 0;
     return 1;
   }
-  float* d = nullptr;
-  if (!dev_alloc(b, &d, (size_t)b->n * frames_per_stream)) return 0;
-  CU_TRY(cudaMemcpy(d, speeds, sizeof(float) * b->n * frames_per_stream, cudaMemcpyHostToDevice));
-  b->d_override = d;
+  if (frames_per_stream < 1) {
+    set_error("speedyBatchOverrideSpeeds: frames_per_stream must be positive");
+    return 0;
+  }
+  const size_t need = (size_t)b->n * frames_per_stream;
+  // kernels of earlier calls may still be reading the previous rows
+  CU_TRY(cudaDeviceSynchronize());
+  if (need > b->override_capacity) {
+    if (b->d_override_buf) {
+      cudaFree(b->d_override_buf);
+      b->allocs.erase(std::remove(b->allocs.begin(), b->allocs.end(), (void*)b->d_override_buf), b->allocs.end());
+      b->d_override_buf = nullptr;
+      b->override_capacity = 0;
+    }
+    float* d = nullptr;
+    if (!dev_alloc(b, &d, need)) return 0;
+    b->d_override_buf = d;
+    b->override_capacity = need;
+  }
+  CU_TRY(cudaMemcpy(b->d_override_buf, speeds, sizeof(float) * need, cudaMemcpyHostToDevice));
+  b->d_override = b->d_override_buf;
   b->override_stride = frames_per_stream;
   return 1;
 }

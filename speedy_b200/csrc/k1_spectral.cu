@@ -1118,13 +1118,8 @@ cudaError_t launch_k1(const K1Params& p, cudaStream_t stream) {
   if (p.g.fft == 480) {
     constexpr int WARPS = 4;
     const size_t smem = k1_smem_bytes_480(WARPS);
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(k1_spectral_480<WARPS>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return e;
-      attr_set = true;
-    }
+    static SmemOptIn opt_480;
+    if (cudaError_t e = opt_480.ensure(k1_spectral_480<WARPS>, smem)) return e;
     const unsigned blocks = (unsigned)((items + WARPS - 1) / WARPS);
     k1_spectral_480<WARPS><<<blocks, WARPS * 32, smem, stream>>>(q);
   } else {
@@ -1167,13 +1162,8 @@ cudaError_t launch_k1(const K1Params& p, cudaStream_t stream) {
       const size_t smem = (size_t)(6 * L + W + (W & 1)) * sizeof(float2) + (size_t)(((W + 3) & ~3) + 3 * HP) * sizeof(float) +
                           (THREADS / 32) * 4 * sizeof(float) +
                           (size_t)((kRun + 1) * p.g.step + p.g.partial + 16) * sizeof(short);
-      static int attr_smem_b = 0;
-      if ((int)smem > attr_smem_b) {
-        cudaError_t e = cudaFuncSetAttribute(k1_spectral_bluestein<THREADS>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        attr_smem_b = (int)smem;
-      }
+      static SmemOptIn opt_b;
+      if (cudaError_t e = opt_b.ensure(k1_spectral_bluestein<THREADS>, smem)) return e;
       k1_spectral_bluestein<THREADS><<<(unsigned)items, THREADS, smem, stream>>>(q);
     } else if (mixed) {
       q.n_factors = np;
@@ -1186,23 +1176,13 @@ cudaError_t launch_k1(const K1Params& p, cudaStream_t stream) {
       const size_t smem = (size_t)(8 * M + 2 * M + W / 2) * sizeof(float2) + (size_t)(4 * W) * sizeof(float) +
                           (THREADS / 32) * 4 * sizeof(float) +
                           (size_t)((kRun + 1) * p.g.step + p.g.partial + 16) * sizeof(short);
-      static int attr_smem_m = 0;
-      if ((int)smem > attr_smem_m) {
-        cudaError_t e = cudaFuncSetAttribute(k1_spectral_mixed<THREADS>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        attr_smem_m = (int)smem;
-      }
+      static SmemOptIn opt_m;
+      if (cudaError_t e = opt_m.ensure(k1_spectral_mixed<THREADS>, smem)) return e;
       k1_spectral_mixed<THREADS><<<(unsigned)items, THREADS, smem, stream>>>(q);
     } else {
       const size_t smem = 2 * (size_t)N * sizeof(float2) + (size_t)N * sizeof(float) + 64 * sizeof(float);
-      static int attr_smem = 0;
-      if ((int)smem > attr_smem) {
-        cudaError_t e = cudaFuncSetAttribute(k1_spectral_generic<THREADS>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        attr_smem = (int)smem;
-      }
+      static SmemOptIn opt_g;
+      if (cudaError_t e = opt_g.ensure(k1_spectral_generic<THREADS>, smem)) return e;
       k1_spectral_generic<THREADS><<<(unsigned)items, THREADS, smem, stream>>>(q);
     }
   }

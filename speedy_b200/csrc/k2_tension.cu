@@ -193,7 +193,8 @@ __global__ void __launch_bounds__(kWarps * 32) k2_tension(K2Params p, float alph
       // soniclib.c:343-345
       float rate = __fadd_rn(__fmul_rn(v, nonlinear), __fmul_rn(Rg, __fsub_rn(1.0f, nonlinear)));
       const int jr = r - rA;  // index among this write's new tensions
-      if (p.override_speeds) rate = p.override_speeds[(size_t)s * p.override_stride + r];
+      // (a stream that runs past the rows it was given falls back to its own speeds)
+      if (p.override_speeds && r < p.override_stride) rate = p.override_speeds[(size_t)s * p.override_stride + r];
       speeds[jr] = rate;
       if (p.tap_tension) p.tap_tension[(size_t)s * p.max_new_frames + jr] = tension;
       if (p.tap_speed) p.tap_speed[(size_t)s * p.max_new_frames + jr] = rate;

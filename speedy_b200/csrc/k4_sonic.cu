@@ -945,10 +945,8 @@ static int k4_buf_frames(const Geometry& g, int n_streams) {
 template <int NW, int MINB, int CH, bool HOSTMAP, bool K16 = false>
 static cudaError_t launch_k4_c(K4Params& p, cudaStream_t stream) {
   const size_t smem = k4_stream_smem(p.g, p.buf_frames);
-  // the shared-memory opt-in is per device (and cheap): set on every launch
-  cudaError_t e = cudaFuncSetAttribute(k4_sonic<NW, MINB, CH, HOSTMAP, K16>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
+  static SmemOptIn opt;  // (one per instantiation)
+  if (cudaError_t e = opt.ensure(k4_sonic<NW, MINB, CH, HOSTMAP, K16>, smem)) return e;
   k4_sonic<NW, MINB, CH, HOSTMAP, K16><<<p.n_streams, NW * 32, smem, stream>>>(p);
   count_launch();
   return cudaGetLastError();
@@ -973,13 +971,18 @@ static cudaError_t launch_k4_t(K4Params& p, cudaStream_t stream) {
 }
 
 cudaError_t launch_k4(const K4Params& p0, cudaStream_t stream) {
-  // long writes of mono streams take the pipelined shape (k4_splice.cu); flushes, short
-  // launches (10 ms streaming writes) and multi-channel streams stay here
+  // The pipelined shape (k4_splice.cu: chain / filler / output warps, TMA bulk loads) is
+  // selected with SPEEDY_K4_PIPELINE=1 (optionally SPEEDY_K4_SPLICE_MIN=<frames>: launches
+  // shorter than that stay here).  Measured (profiles/README.md): with the same 16 kHz pitch
+  // search (amdf16.cuh) in both, the three-warp CTA is held to 80 registers by the per-
+  // scheduler register file at 7 streams per SM and its helper warps compete with the
+  // analysis kernels for issue slots, so the one-warp shape is the faster step; flushes,
+  // short launches and multi-channel streams always run here.
   {
-    static const int legacy = getenv("SPEEDY_K4_LEGACY") ? atoi(getenv("SPEEDY_K4_LEGACY")) : 0;
-    static const long long min_frames = getenv("SPEEDY_K4_SPLICE_MIN") ? atoll(getenv("SPEEDY_K4_SPLICE_MIN")) : -1;
+    const int pipeline = getenv("SPEEDY_K4_PIPELINE") ? atoi(getenv("SPEEDY_K4_PIPELINE")) : 0;
+    const long long min_frames = getenv("SPEEDY_K4_SPLICE_MIN") ? atoll(getenv("SPEEDY_K4_SPLICE_MIN")) : -1;
     const bool short_launch = p0.flush || p0.frames - p0.done <= (min_frames >= 0 ? min_frames : (long long)p0.g.rate);
-    if (!legacy && !short_launch && p0.threads_per_stream <= 32 && k4_splice_supported(p0)) {
+    if (pipeline && !short_launch && p0.threads_per_stream <= 32 && k4_splice_supported(p0)) {
       return launch_k4_splice(p0, stream);
     }
   }

@@ -1223,13 +1223,11 @@ cudaError_t launch_k4_splice(const K4Params& p0, cudaStream_t stream) {
   SpliceLayout L = make_layout(g.max_period, g.max_required, g.skip, g.channels, depth, nsw_override);
   if (const char* e = getenv("SPEEDY_K4_POLL_NS")) L.poll_ns = atoi(e) > 0 ? atoi(e) : 500;
   L.out_vec = ((p.out_capacity * g.channels) % 8 == 0 && (reinterpret_cast<size_t>(p.out) & 15) == 0) ? 1 : 0;
-  // the shared-memory opt-in is per device (and cheap): set it on every launch
   // 16 kHz streams take the instantiation with compile-time geometry
   const bool skip4 = !tuned && g.channels == 1 && g.rate == 16000 && g.step == 160 && g.min_period == 40 &&
                      g.max_period == 246 && g.skip == 4;  // kLay16 is this layout
-  cudaError_t e = skip4 ? cudaFuncSetAttribute(k4_splice<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total)
-                        : cudaFuncSetAttribute(k4_splice<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
-  if (e != cudaSuccess) return e;
+  static SmemOptIn opt16, opt;
+  if (cudaError_t e = skip4 ? opt16.ensure(k4_splice<true>, L.total) : opt.ensure(k4_splice<false>, L.total)) return e;
   if (skip4) k4_splice<true><<<p.n_streams, kThreads, L.total, stream>>>(p, L);
   else k4_splice<false><<<p.n_streams, kThreads, L.total, stream>>>(p, L);
   count_launch();

@@ -8,6 +8,8 @@
 // Scratch rows stay indexed from the first new frame of the whole write.
 #pragma once
 
+#include <atomic>
+
 #include "common.cuh"
 
 #ifndef K1_RUN
@@ -19,6 +21,30 @@ namespace speedy {
 constexpr int kMaxFactors = 16;
 
 void count_launch();
+
+// Opt a kernel in to `bytes` of dynamic shared memory on the CURRENT device.  The attribute
+// is per device and launches may come from several host threads, so the largest size
+// already granted is cached per device in atomics (one cache per call site).
+constexpr int kMaxDevices = 64;
+struct SmemOptIn {
+  std::atomic<int> granted[kMaxDevices];
+  template <class Kernel>
+  cudaError_t ensure(Kernel kernel, size_t bytes) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const bool cached = dev >= 0 && dev < kMaxDevices;
+    if (cached && granted[dev].load(std::memory_order_acquire) >= (int)bytes) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return e;
+    if (cached) {
+      int seen = granted[dev].load(std::memory_order_relaxed);
+      while (seen < (int)bytes && !granted[dev].compare_exchange_weak(seen, (int)bytes, std::memory_order_release)) {
+      }
+    }
+    return cudaSuccess;
+  }
+};
 
 // ---- K1: spectrogram, frame energy, raw spectral difference ---------------
 struct K1Params {
