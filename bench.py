@@ -37,16 +37,50 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-RATE = 16000
-CHANNELS = 1
-STREAMS = int(os.environ.get("SPEEDY_BENCH_STREAMS", 1024))
-SECONDS = int(os.environ.get("SPEEDY_BENCH_SECONDS", 60))
-SPEED = 2.0
 NONLINEAR = 1.0
 FEEDBACK = 0.1  # library default (soniclib.c:122)
-WORKLOAD = "%d synthetic 16 kHz mono streams x %d s, nonlinear %.1fx, per GPU" % (STREAMS, SECONDS, SPEED)
 METRIC = "batched real-time factor (audio-seconds processed per second)"
 UNIT = "audio-s/s"
+
+# BASELINE.json configurations, per GPU (streams are independent: weak scaling, every rank gets
+# its own shard, no collective on the data path).  Config 2 is the default and the one the
+# metric is quoted on; 3-5 are selected with --config.
+#   2  1024 x 60 s, 16 kHz mono, 2.0x
+#   3  65536 x 30 s, 16 kHz mono, 3.5x over 8 GPUs: the per-GPU shard, 8192 x 30 s
+#   4  4096 x 120 s, 48 kHz stereo, 1.5x: a 1024-stream slab per GPU (23.6 GB in, 15.7 GB out);
+#      the end-to-end leg moves it through speedyBatchProcess in 256-stream slabs
+#   5  16384 sessions fed 10 ms chunks, 2.5x: a step is ONE 10 ms write of every session
+CONFIGS = {
+    2: dict(rate=16000, channels=1, streams=1024, seconds=60, speed=2.0, chunk=None, e2e_slab=None),
+    3: dict(rate=16000, channels=1, streams=8192, seconds=30, speed=3.5, chunk=None, e2e_slab=None),
+    4: dict(rate=48000, channels=2, streams=1024, seconds=120, speed=1.5, chunk=None, e2e_slab=256),
+    5: dict(rate=16000, channels=1, streams=16384, seconds=8, speed=2.5, chunk=160, e2e_slab=None),
+}
+CFG = None  # the selected entry, with the SPEEDY_BENCH_STREAMS / SPEEDY_BENCH_SECONDS overrides applied
+
+
+def select_config(num):
+    global CFG, RATE, CHANNELS, STREAMS, SECONDS, SPEED, WORKLOAD
+    CFG = dict(CONFIGS[num], number=num)
+    if os.environ.get("SPEEDY_BENCH_STREAMS"):
+        CFG["streams"] = int(os.environ["SPEEDY_BENCH_STREAMS"])
+    if os.environ.get("SPEEDY_BENCH_SECONDS"):
+        CFG["seconds"] = int(os.environ["SPEEDY_BENCH_SECONDS"])
+    RATE, CHANNELS, STREAMS, SECONDS, SPEED = CFG["rate"], CFG["channels"], CFG["streams"], CFG["seconds"], CFG["speed"]
+    layout = "%g kHz %s" % (RATE / 1000.0, "mono" if CHANNELS == 1 else "stereo")
+    if CFG["chunk"]:
+        WORKLOAD = ("config %d: %d concurrent %s sessions fed %d-frame (10 ms) writes, nonlinear %.1fx, per GPU"
+                    % (num, STREAMS, layout, CFG["chunk"], SPEED))
+    else:
+        WORKLOAD = "%d synthetic %s streams x %d s, nonlinear %.1fx, per GPU" % (STREAMS, layout, SECONDS, SPEED)
+        if num != 2:
+            WORKLOAD = "config %d: " % num + WORKLOAD
+
+
+select_config(2)
+
+
+NCU_SUMMARY = "r02_kernels.json" if os.path.exists(os.path.join(ROOT, "profiles", "r02_kernels.json")) else "r01_kernels.json"
 
 
 def ncu_traffic(kernel_substr):
@@ -54,7 +88,7 @@ def ncu_traffic(kernel_substr):
     from the committed ncu --set full capture (profiles/r01_kernels.json, taken with
     SPEEDY_B200_WRITE_PARTS=1 so that one launch covers the step)."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_kernels.json")) as f:
+        with open(os.path.join(ROOT, "profiles", NCU_SUMMARY)) as f:
             ks = json.load(f)["kernels"]
         best = None
         for k in ks:
@@ -157,6 +191,11 @@ class ClockSampler:
 # --------------------------------------------------------------------------
 # CPU reference arm
 # --------------------------------------------------------------------------
+CPU_BUILD = ("gcc -O2 -ffp-contract=off (no -march); reference speedy.c + soniclib.c unmodified, FFTW-double "
+             "configuration; the FFT behind fftw3.h and upstream Sonic are this repo's restatements "
+             "(oracle/fft_oracle.c, oracle/sonic_oracle.c), not FFTW / waywardgeek/sonic")
+
+
 def load_reference():
     """oracle/_ref (the reference's own code); falls back to the restated port."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -172,7 +211,8 @@ def cpu_run(ol, kind, pcm, threads):
     counts = np.zeros(n, np.int64)
     t0 = time.perf_counter()
     if kind == "reference":
-        ol.ref("fftw").ref_run_batch(ol.sptr(pcm), frames, n, RATE, ch, SPEED, NONLINEAR, FEEDBACK, 1000, None, 0,
+        ol.ref("fftw").ref_run_batch(ol.sptr(pcm), frames, n, RATE, ch, SPEED, NONLINEAR, FEEDBACK,
+                                     CFG["chunk"] or 1000, None, 0,
                                      counts.ctypes.data_as(ol.c_long_p), threads)
     else:
         out = np.zeros((n, frames + 4096, ch), np.int16)
@@ -196,20 +236,23 @@ def run_reference_arm(args):
     cores = os.cpu_count() or 1
     # bounded sample: two streams per core of the same synthetic workload per step
     n = 2 * cores
-    pcm = cpu_sample(ol, n, SECONDS)
+    secs = min(SECONDS, 60)
+    pcm = cpu_sample(ol, n, secs)
     for _ in range(args.warmup):
         cpu_run(ol, kind, pcm[:cores], cores)
     times = [cpu_run(ol, kind, pcm, cores) for _ in range(args.steps)]
     dt = sum(times) / len(times)
-    value = n * SECONDS / dt
-    sample = "%d of the workload's streams x %d s per step (ids 0..%d), %d threads" % (n, SECONDS, n - 1, cores)
+    value = n * secs / dt
+    sample = "%d of the workload's streams x %d s per step (ids 0..%d), %d threads, writes of %d frames" % (
+        n, secs, n - 1, cores, CFG["chunk"] or 1000)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32+i16", "data": "synthetic",
         "config": {"workload": WORKLOAD, "note": "CPU reference: unmodified speedy.c + soniclib.c "
                    "(FFT and Sonic restated, see oracle/), all host cores, bounded sample"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
+                         "build": CPU_BUILD},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -303,21 +346,34 @@ def run_cuda_arm(args):
     assert not (status & (sb.STATUS_OUTPUT_OVERFLOW | sb.STATUS_INPUT_OVERFLOW)).any(), "stream overflow"
 
     # ---- end to end: host buffers through speedyBatchProcess ----------------
-    h_in = torch.empty((n, frames, CHANNELS), dtype=torch.int16, pin_memory=True)
-    h_in.copy_(d_in)
-    h_out = torch.empty((n, out_cap, CHANNELS), dtype=torch.int16, pin_memory=True)
-    h_counts = torch.zeros(n, dtype=torch.int32)
+    # (config 4: in slabs of e2e_slab streams, the way a 94 GB job is tiled through the device)
+    slab = CFG["e2e_slab"] or n
+    n_slabs = n // slab
+    eb = batch if slab == n else sb.Batch(slab, RATE, CHANNELS, speed=SPEED, nonlinear=NONLINEAR, feedback=FEEDBACK,
+                                          device=local, max_write_frames=frames, out_capacity=out_cap)
+    h_in = torch.empty((slab, frames, CHANNELS), dtype=torch.int16, pin_memory=True)
+    h_in.copy_(d_in[:slab])
+    h_out = torch.empty((slab, out_cap, CHANNELS), dtype=torch.int16, pin_memory=True)
+    h_counts = torch.zeros(slab, dtype=torch.int32)
     e2e_steps = max(1, min(args.steps, 5))
-    for _ in range(2):
-        batch.process_ptr(h_in, frames, h_out, out_cap, h_counts)
+
+    def e2e_step():
+        for _ in range(n_slabs):
+            eb.process_ptr(h_in, frames, h_out, out_cap, h_counts)
+
+    for _ in range(2 if n_slabs == 1 else 1):
+        e2e_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        batch.process_ptr(h_in, frames, h_out, out_cap, h_counts)
+        e2e_step()
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     e2e_out_frames = int(h_counts.sum().item())
-    assert e2e_out_frames == out_frames, (e2e_out_frames, out_frames)
+    if n_slabs == 1:
+        assert e2e_out_frames == out_frames, (e2e_out_frames, out_frames)
+    else:
+        assert e2e_out_frames > 0
 
     # ---- max over ranks -----------------------------------------------------
     t = torch.tensor([elapsed_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
@@ -342,10 +398,10 @@ def run_cuda_arm(args):
         dom_ms = sonic_ms if dominant == "sonic" else kt["spectral"]
         achieved = alg[dominant] / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0
         roofline = {
-            "bound": "hbm", "kernel": "k4_sonic" if dominant == "sonic" else "k1_spectral_480",
+            "bound": "hbm", "kernel": "k4_sonic" if dominant == "sonic" else ("k1_spectral_480" if RATE == 16000 else "k1_spectral_mixed"),
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": ncu_traffic("k4_sonic" if dominant == "sonic" else "k1_spectral") if n == 1024 and SECONDS == 60 else None,
-            "traffic_source": "profiles/r01_kernels.json (ncu --set full, one launch per step)",
+            "traffic": ncu_traffic("k4_sonic" if dominant == "sonic" else "k1_spectral") if CFG["number"] == 2 and n == 1024 and SECONDS == 60 else None,
+            "traffic_source": "profiles/%s (ncu --set full, one launch per step)" % NCU_SUMMARY,
             "peak_source": peak_src,
             "algorithmic_bytes_per_launch": alg[dominant], "kernel_ms": dom_ms,
             "kernel_ms_all": kt,
@@ -357,30 +413,180 @@ def run_cuda_arm(args):
         if world == 1 and not args.no_cpu_baseline:
             ol, kind = load_reference()
             cores = os.cpu_count() or 1
-            per_core = 16  # ~45 CPU-seconds of work in total, a few seconds of wall time
+            per_core = 16 if CHANNELS == 1 else 2  # a few seconds of wall time
             ns = min(n, per_core * cores)
-            pcm = h_in[:ns].numpy()
-            if ns > n:
-                pcm = cpu_sample(ol, ns, SECONDS)
+            cpu_secs = min(SECONDS, 60)
+            pcm = h_in[:ns, :cpu_secs * RATE].numpy()
             dt = cpu_run(ol, kind, np.ascontiguousarray(pcm), cores)
-            cpu_baseline = {"value": ns * SECONDS / dt, "unit": UNIT, "cores": cores, "kind": kind,
+            cpu_baseline = {"value": ns * cpu_secs / dt, "unit": UNIT, "cores": cores, "kind": kind,
                             "sample": "%d of the %d streams x %d s (%.1f s of wall time on %d threads)"
-                                      % (ns, n, SECONDS, dt, cores)}
+                                      % (ns, n, cpu_secs, dt, cores), "build": CPU_BUILD}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32+i16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "streams_per_gpu": n, "seconds_per_stream": SECONDS,
+            "config": {"workload": WORKLOAD, "baseline_config": CFG["number"], "streams_per_gpu": n, "seconds_per_stream": SECONDS,
                        "sample_rate": RATE, "channels": CHANNELS, "speed": SPEED, "nonlinear_factor": NONLINEAR,
                        "feedback_strength": FEEDBACK, "output_frames_per_step": out_frames,
                        "cache": "inputs (%.2f GB per step) exceed the 126 MB L2" % (in_bytes / 1e9),
                        "sharding": "independent streams per rank, no collective"},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes + 4 * n,
-                    "api": "speedyBatchProcess (pinned host buffers)"},
+                    "api": "speedyBatchProcess (pinned host buffers)" + ("" if n_slabs == 1 else ", %d slabs of %d streams" % (n_slabs, slab))},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
+            "clocks": clocks,
+            "build": sb.lib().speedyBatchBuildInfo().decode(),
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def _percentiles(xs):
+    xs = sorted(xs)
+    pick = lambda q: xs[min(len(xs) - 1, int(q * len(xs)))]
+    return {"p50": pick(0.50), "p90": pick(0.90), "p99": pick(0.99), "max": xs[-1], "n": len(xs)}
+
+
+def run_cuda_streaming(args):
+    """Config 5: every session is fed one 10 ms chunk per step (speedyBatchWriteDevice on a
+    strided view of the resident input) and its output is drained (speedyBatchReadDevice).
+    `value` is throughput with the input resident; `e2e` feeds HOST chunks (speedyBatchWrite /
+    speedyBatchRead: H2D of the chunk, D2H of the produced audio, inside the timed region) and
+    reports the per-step latency a session sees (p50 / p99)."""
+    import torch
+    import speedy_b200 as sb
+
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the CUDA arm has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n, chunk = STREAMS, CFG["chunk"]
+    chunks_total = SECONDS * RATE // chunk          # chunks of resident input per session
+    frames = chunks_total * chunk
+    steps = args.steps * 40                         # a step is one 10 ms write of every session
+    warm = max(args.warmup, 3) * 40
+    assert warm + steps <= chunks_total, "raise SPEEDY_BENCH_SECONDS"
+    out_cap = 8192                                  # drained every step
+    batch = sb.Batch(n, RATE, CHANNELS, speed=SPEED, nonlinear=NONLINEAR, feedback=FEEDBACK, device=local,
+                     max_write_frames=chunk, out_capacity=out_cap)
+    tstream = torch.cuda.Stream()
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    d_in = torch.empty((n, frames, CHANNELS), dtype=torch.int16, device="cuda")
+    sb.synth_device(d_in, rank * n, n, RATE, CHANNELS, frames, stream=stream)
+    d_out = torch.empty((n, out_cap, CHANNELS), dtype=torch.int16, device="cuda")
+    d_cnt = torch.zeros(n, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+
+    def step(k):
+        batch.write_device(d_in[:, k * chunk:], frames, chunk, None, stream)
+        batch.read_device(d_out, out_cap, d_cnt, stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    for k in range(warm):
+        step(k)
+    barrier()
+    sampler.wait_first()
+    batch.set_profiling(True)
+    launches0 = sb.kernel_launches()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    wall0 = time.time()
+    ev0.record()
+    for k in range(warm, warm + steps):
+        step(k)
+    ev1.record()
+    barrier()
+    wall1 = time.time()
+    launches = sb.kernel_launches() - launches0
+    elapsed_ms = ev0.elapsed_time(ev1)
+    kt = {k: v / steps for k, v in batch.kernel_times().items()}
+    batch.set_profiling(False)
+    clocks = sampler.stop(wall0, wall1)
+    status = batch.status()
+    assert not (status & (sb.STATUS_OUTPUT_OVERFLOW | sb.STATUS_INPUT_OVERFLOW)).any(), "stream overflow"
+
+    # per-step latency with the input resident: launch -> output counts visible to the host
+    batch.reset(stream)
+    lat_dev = []
+    for k in range(warm + steps):
+        t0 = time.perf_counter()
+        step(k)
+        tstream.synchronize()
+        if k >= warm:
+            lat_dev.append((time.perf_counter() - t0) * 1e3)
+
+    # ---- end to end: host chunks in, host audio out, per step ----------------
+    h_in = torch.empty((n, frames, CHANNELS), dtype=torch.int16, pin_memory=True)
+    h_in.copy_(d_in)
+    h_out = torch.empty((n, out_cap, CHANNELS), dtype=torch.int16, pin_memory=True)
+    h_cnt = torch.zeros(n, dtype=torch.int32)
+    batch.reset(stream)
+    torch.cuda.synchronize()
+    lat_e2e = []
+    out_frames = 0
+    t_all = None
+    for k in range(warm + steps):
+        if k == warm:
+            barrier()
+            t_all = time.perf_counter()
+        t0 = time.perf_counter()
+        batch.write_ptr(h_in, frames, chunk, k * chunk)
+        batch.read_ptr(h_out, out_cap, h_cnt)
+        if k >= warm:
+            lat_e2e.append((time.perf_counter() - t0) * 1e3)
+            out_frames += int(h_cnt.sum())
+    e2e_ms = (time.perf_counter() - t_all) * 1e3 / steps
+
+    t = torch.tensor([elapsed_ms, e2e_ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms, e2e_ms = t.tolist()
+    ms_per_step = elapsed_ms / steps
+    audio_s = world * n * chunk / RATE
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        in_bytes = n * chunk * CHANNELS * 2
+        out_bytes = int(out_frames / steps) * CHANNELS * 2
+        dom = max(("spectral", "tension", "sonic", "tail"), key=lambda k: kt[k])
+        line = {
+            "metric": METRIC, "value": audio_s / (ms_per_step / 1e3), "unit": UNIT, "n_gpus": world, "steps": steps,
+            "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32+i16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "baseline_config": 5, "sessions_per_gpu": n, "chunk_frames": chunk,
+                       "speed": SPEED, "nonlinear_factor": NONLINEAR, "feedback_strength": FEEDBACK,
+                       "real_time_budget_ms_per_step": 1e3 * chunk / RATE,
+                       "cache": "%.1f MB of new input per step, %.2f GB of resident input cycled" % (in_bytes / 1e6, n * frames * 2 / 1e9)},
+            "latency_ms": {"resident": _percentiles(lat_dev), "e2e": _percentiles(lat_e2e),
+                           "what": "host-observed time of one step (write + drain + synchronise) for all sessions"},
+            "e2e": {"value": audio_s / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes + 4 * n,
+                    "api": "speedyBatchWrite + speedyBatchRead (host chunks)"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": (in_bytes + out_bytes) / (kt[dom] / 1e3) / 1e9 if kt[dom] > 0 else 0.0,
+                         "peak": peak, "unit": "GB/s",
+                         "frac": ((in_bytes + out_bytes) / (kt[dom] / 1e3) / 1e9 / peak) if kt[dom] > 0 else 0.0,
+                         "traffic": None, "peak_source": peak_src, "kernel_ms_all": kt,
+                         "note": "launch- and latency-bound: four short launches per 10 ms step"},
+            "cpu_baseline": None,
             "clocks": clocks,
             "build": sb.lib().speedyBatchBuildInfo().decode(),
         }
@@ -399,9 +605,14 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--threads-per-stream", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS),
+                    help="BASELINE.json configuration (default 2: the one the metric is quoted on)")
     args = ap.parse_args()
+    select_config(args.config)
     if args.impl == "reference":
         return run_reference_arm(args)
+    if CFG["chunk"]:
+        return run_cuda_streaming(args)
     return run_cuda_arm(args)
 
 

@@ -256,6 +256,16 @@ class Batch:
         self._ok(lib().speedyBatchGetKernelTimes(self.h, ms.ctypes.data), "speedyBatchGetKernelTimes")
         return dict(zip(("spectral", "tension", "sonic", "tail", "flush_sonic"), ms.tolist()))
 
+    def write_ptr(self, h_in, stride_frames, frames, offset_frames=0):
+        """speedyBatchWrite on a raw host address (e.g. a pinned torch tensor): stream s starts
+        at h_in + (s * stride_frames + offset_frames) frames."""
+        addr = _ptr(h_in) + offset_frames * self.channels * 2
+        self._ok(lib().speedyBatchWrite(self.h, addr, stride_frames, frames, None), "speedyBatchWrite")
+
+    def read_ptr(self, h_out, stride_frames, h_counts):
+        """speedyBatchRead into raw host addresses (int16 [n, stride_frames, channels], int32 [n])."""
+        self._ok(lib().speedyBatchRead(self.h, _ptr(h_out), stride_frames, _ptr(h_counts)), "speedyBatchRead")
+
     def process_ptr(self, h_in, frames, h_out, out_stride, h_counts):
         """speedyBatchProcess on raw host addresses (e.g. pinned torch tensors)."""
         self._ok(lib().speedyBatchProcess(self.h, _ptr(h_in), frames, _ptr(h_out), out_stride, _ptr(h_counts)),

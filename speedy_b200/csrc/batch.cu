@@ -124,6 +124,30 @@ __global__ void __launch_bounds__(256) read_copy_kernel(const int16_t* out, long
   }
 }
 
+// The same with one warp per stream: many streams with little pending output each (the 10 ms
+// streaming step: a grid of 32 x n blocks would be half a million nearly empty CTAs).
+__global__ void __launch_bounds__(256) read_copy_warp_kernel(const int16_t* out, long long cap, int channels,
+                                                             const int* pending, int16_t* dst, long long dst_stride,
+                                                             int n) {
+  const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (s >= n) return;
+  const int lane = threadIdx.x & 31;
+  long long c = pending[s];
+  if (c > dst_stride) c = dst_stride;
+  const long long total = c * channels;
+  const int16_t* src = out + (size_t)s * cap * channels;
+  int16_t* d = dst + (size_t)s * dst_stride * channels;
+  if (((((size_t)src) | ((size_t)d)) & 15) == 0) {
+    const long long nv = total / 8;
+    const int4* sv = reinterpret_cast<const int4*>(src);
+    int4* dv = reinterpret_cast<int4*>(d);
+    for (long long i = lane; i < nv; i += 32) dv[i] = sv[i];
+    for (long long i = nv * 8 + lane; i < total; i += 32) d[i] = src[i];
+  } else {
+    for (long long i = lane; i < total; i += 32) d[i] = src[i];
+  }
+}
+
 // speedyBatchProcess: move what every stream produced since the last call,
 // out[s][done[s] .. upto[s]), straight into the caller's pinned host buffer (a
 // device-accessible pointer under unified addressing) with 16-byte stores where the
@@ -856,6 +880,9 @@ int speedyBatchWriteDevice(speedyBatch b, const int16_t* d_in, int64_t stride_fr
   if (const char* e = getenv("SPEEDY_B200_WRITE_PARTS")) parts = atoi(e) > 0 ? atoi(e) : parts;
   if (parts > kPipeEvents - 2) parts = kPipeEvents - 2;
   if (parts == 1) {
+    // (Replaying these four launches as a CUDA graph was measured on the 10 ms streaming step,
+    // 16384 sessions: 0.264 ms per step with the graph, 0.265 without.  Queued asynchronously the
+    // step is bound by the four kernels' own device time, not by launch overhead; not kept.)
     if (!launch_analysis(w, 0, frames, st) || !launch_resynthesis(w, 0, frames, st)) return 0;
     return launch_write_tail(w, st);
   }
@@ -911,9 +938,15 @@ int speedyBatchReadDevice(speedyBatch b, int16_t* d_out, int64_t stride_frames, 
   CU_TRY(cudaSetDevice(b->cfg.device));
   cudaStream_t st = pick_stream(b, cuda_stream);
   if (d_out) {
-    dim3 grid(32, b->n);
-    read_copy_kernel<<<grid, 256, 0, st>>>(b->d_out, b->out_capacity, b->g.channels, b->st.out_count, d_out,
-                                           stride_frames);
+    if (b->n >= 2048 && b->out_capacity * b->g.channels <= 65536) {
+      // many streams, little room per stream: one warp each
+      read_copy_warp_kernel<<<(b->n + 7) / 8, 256, 0, st>>>(b->d_out, b->out_capacity, b->g.channels, b->st.out_count,
+                                                           d_out, stride_frames, b->n);
+    } else {
+      dim3 grid(32, b->n);
+      read_copy_kernel<<<grid, 256, 0, st>>>(b->d_out, b->out_capacity, b->g.channels, b->st.out_count, d_out,
+                                             stride_frames);
+    }
     count_launch();
   }
   read_finish_kernel<<<(b->n + 127) / 128, 128, 0, st>>>(b->n, b->st.out_count, b->st.status, d_counts,
