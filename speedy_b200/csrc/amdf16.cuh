@@ -16,6 +16,17 @@ namespace amdf16 {
 
 constexpr unsigned kFull = 0xffffffffu;
 
+#ifdef K4_TIMING
+// developer build: cycles of the search's phases (0 decimate, 1 coarse blocks, 2 coarse pick,
+// 3 fine blocks, 4 fine pick), accumulated by lane 0 of the stream that has k.timing set
+static __device__ unsigned long long g_amdf_cycles[8];
+#define AT_BEGIN() long long _at0 = clock64()
+#define AT_MARK(slot) do { const long long _t1 = clock64(); if (k.lane == 0 && k.timing) atomicAdd(&g_amdf_cycles[slot], (unsigned long long)(_t1 - _at0)); _at0 = _t1; } while (0)
+#else
+#define AT_BEGIN() do {} while (0)
+#define AT_MARK(slot) do {} while (0)
+#endif
+
 // The 16 |a - b| terms of one aligned block of four samples for the four lags pg .. pg+3
 // (pg a multiple of four), every sample valid for every lag.
 __device__ __forceinline__ void sad16(const int4& av, const int4& b0, const int4& b1, unsigned (&d)[4]) {
@@ -156,6 +167,7 @@ __device__ __forceinline__ int search(const Ctx& k, const int* arr, int off, int
                                       int G, int* minDiff, int* maxDiff) {
   constexpr bool WANT_DIFFS = FINE;
   unsigned d[4] = {0u, 0u, 0u, 0u};
+  AT_BEGIN();
   if (live) {
     const int B0 = off & ~3, hd = off & 3;
     const int* base = arr + B0;
@@ -173,6 +185,7 @@ __device__ __forceinline__ int search(const Ctx& k, const int* arr, int off, int
     const int base = lo & ~3;
     if (live) *reinterpret_cast<uint4*>(part + sub * 64 + (pg - base)) = make_uint4(d[0], d[1], d[2], d[3]);
     __syncwarp();
+    AT_MARK(FINE ? 3 : 1);
     unsigned sa = 0u, sb = 0u;
 #pragma unroll
     for (int r = 0; r < ROWS; r++) {
@@ -217,6 +230,10 @@ __device__ __forceinline__ int search(const Ctx& k, const int* arr, int off, int
       *minDiff = md;
       *maxDiff = worst_diff >= (unsigned)(3 * md + 1) * (unsigned)worst ? 3 * md + 1 : 0;
     }
+#ifdef K4_TIMING
+    _at0 += (best & 0);  // (the pick's result is needed before the clock is read)
+#endif
+    AT_MARK(FINE ? 4 : 2);
     return best;
   }
 }
@@ -225,6 +242,7 @@ __device__ __forceinline__ int search(const Ctx& k, const int* arr, int off, int
 // from five aligned 16-byte loads, C integer division as (v + (v < 0 ? 3 : 0)) >> 2.
 template <class Ctx>
 __device__ __forceinline__ void decimate(const Ctx& k, int off) {
+  AT_BEGIN();
   __syncwarp();  // every lane is done reading the previous decimated copy
   {
     const int r = off & 3;
@@ -253,6 +271,7 @@ __device__ __forceinline__ void decimate(const Ctx& k, int off) {
     reinterpret_cast<int4*>(k.ds())[k.lane] = o;
   }
   __syncwarp();
+  AT_MARK(0);
 }
 
 // findPitchPeriod at window offset `off`: coarse pass on the decimated copy (a static lane

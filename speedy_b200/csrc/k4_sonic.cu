@@ -1007,10 +1007,16 @@ cudaError_t launch_k4(const K4Params& p0, cudaStream_t stream) {
 #ifdef K4_TIMING
 // developer build only (SPEEDY_K4_TIMING=1): read / reset the per-phase cycle counters
 extern "C" void speedyDebugK4Cycles(unsigned long long* out, int reset) {
-  if (out) cudaMemcpyFromSymbol(out, speedy::g_k4_cycles, sizeof(unsigned long long) * 16);
+  if (out) {
+    cudaMemcpyFromSymbol(out, speedy::g_k4_cycles, sizeof(unsigned long long) * 16);
+    unsigned long long a[8];  // the 16 kHz search's own phases (amdf16.cuh)
+    cudaMemcpyFromSymbol(a, speedy::amdf16::g_amdf_cycles, sizeof(a));
+    for (int i = 0; i < 5; i++) out[1 + i] += a[i];
+  }
   if (reset) {
     unsigned long long z[16] = {0};
     cudaMemcpyToSymbol(speedy::g_k4_cycles, z, sizeof(z));
+    cudaMemcpyToSymbol(speedy::amdf16::g_amdf_cycles, z, sizeof(unsigned long long) * 8);
   }
 }
 #endif

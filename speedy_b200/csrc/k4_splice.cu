@@ -1239,10 +1239,18 @@ cudaError_t launch_k4_splice(const K4Params& p0, cudaStream_t stream) {
 #ifdef K4_TIMING
 // developer build only (SPEEDY_K4_TIMING=1): read / reset the chain warp's per-phase cycle counters
 extern "C" void speedyDebugK4SpliceCycles(unsigned long long* out, int reset) {
-  if (out) cudaMemcpyFromSymbol(out, speedy::g_k4s_cycles, sizeof(unsigned long long) * 16);
+  if (out) {
+    cudaMemcpyFromSymbol(out, speedy::g_k4s_cycles, sizeof(unsigned long long) * 16);
+    unsigned long long a[8];  // the 16 kHz search's own phases (amdf16.cuh)
+    cudaMemcpyFromSymbol(a, speedy::amdf16::g_amdf_cycles, sizeof(a));
+    out[1] += a[0];
+    out[2] += a[1] + a[2];
+    out[4] += a[3] + a[4];
+  }
   if (reset) {
     unsigned long long z[16] = {0};
     cudaMemcpyToSymbol(speedy::g_k4s_cycles, z, sizeof(z));
+    cudaMemcpyToSymbol(speedy::amdf16::g_amdf_cycles, z, sizeof(unsigned long long) * 8);
   }
 }
 #endif
