@@ -44,7 +44,7 @@ for loc, (s, n) in sorted(agg.items(), key=lambda kv: -kv[1][keyi])[:topn]:
     if loc is None: print(s, n, None); continue
     f, ln = loc
     if f not in src:
-        try: src[f] = open('speedy_b200/csrc/' + f).read().split('\n')
+        try: src[f] = open(os.environ.get('SRC_DIR','speedy_b200/csrc/') + f).read().split('\n')
         except Exception: src[f] = []
     text = src[f][ln-1].strip() if 0 < ln <= len(src[f]) else ''
     top_st = ','.join('%s:%d' % (k.replace('stall_', ''), v) for k, v in stall_agg[loc].most_common(3))

@@ -6,7 +6,7 @@
 //   int lane, cGi, cSub, cG (coarse: group, lane in group, lanes of the group), fg, fGi0 (fine);
 //   int prevPeriod, prevMinDiff;
 //   int* win() / ds() (32-bit mono window, decimated copy), float* rcp() (1 / lag table),
-//   unsigned* part() (7 x 64 per-lag partial sums; the first four rows zero at start).
+//   unsigned* part() (kPartWords per-lag partial sums, 7 rows of kPartStride; zero at start).
 #pragma once
 
 #include <cuda_runtime.h>
@@ -15,6 +15,12 @@ namespace speedy {
 namespace amdf16 {
 
 constexpr unsigned kFull = 0xffffffffu;
+// Row stride of the per-lag partial sums (four coarse rows, three fine rows of up to 64 lags).
+// 76 words = 19 sixteen-byte slots: the 16-byte stores of a quarter-warp (lanes enumerate
+// lag group x lane-in-group) then fall into distinct bank groups (4 - 5 wavefronts per store,
+// 12 with a stride of 64).
+constexpr int kPartStride = 76;
+constexpr int kPartWords = 7 * kPartStride;
 
 #ifdef K4_TIMING
 // developer build: cycles of the search's phases (0 decimate, 1 coarse blocks, 2 coarse pick,
@@ -181,16 +187,16 @@ __device__ __forceinline__ int search(const Ctx& k, const int* arr, int off, int
     // back one lag per lane (lag base + lane, and base + 32 + lane): no shuffle tree, no
     // four-lags-per-leader selects.  Rows a group has no lane for stay zero (coarse pass: the
     // lane assignment is static); lags outside [lo, hi] are masked below.
-    unsigned* part = k.part() + (WANT_DIFFS ? 4 * 64 : 0);
+    unsigned* part = k.part() + (WANT_DIFFS ? 4 * kPartStride : 0);
     const int base = lo & ~3;
-    if (live) *reinterpret_cast<uint4*>(part + sub * 64 + (pg - base)) = make_uint4(d[0], d[1], d[2], d[3]);
+    if (live) *reinterpret_cast<uint4*>(part + sub * kPartStride + (pg - base)) = make_uint4(d[0], d[1], d[2], d[3]);
     __syncwarp();
     AT_MARK(FINE ? 3 : 1);
     unsigned sa = 0u, sb = 0u;
 #pragma unroll
     for (int r = 0; r < ROWS; r++) {
-      sa += part[r * 64 + k.lane];
-      sb += part[r * 64 + 32 + k.lane];
+      sa += part[r * kPartStride + k.lane];
+      sb += part[r * kPartStride + 32 + k.lane];
     }
     __syncwarp();  // (the next search of this kind rewrites the rows)
     const int la = base + k.lane, lb = la + 32;
@@ -238,37 +244,39 @@ __device__ __forceinline__ int search(const Ctx& k, const int* arr, int off, int
   }
 }
 
-// Upstream downSampleInput: four frames per value, every lane makes four consecutive values
-// from five aligned 16-byte loads, C integer division as (v + (v < 0 ? 3 : 0)) >> 2.
+// Upstream downSampleInput: four frames per value, C integer division as
+// (v + (v < 0 ? 3 : 0)) >> 2.  Lane l loads the aligned vectors l, l + 32, l + 64, l + 96 of
+// the span (consecutive 16-byte slots across the warp: no bank conflicts) and splits each at
+// the span's offset inside a vector; a value is the upper part of its vector plus the lower
+// part of the next one, which the neighbouring lane holds.
 template <class Ctx>
 __device__ __forceinline__ void decimate(const Ctx& k, int off) {
   AT_BEGIN();
   __syncwarp();  // every lane is done reading the previous decimated copy
   {
     const int r = off & 3;
-    const int4* p = reinterpret_cast<const int4*>(k.win() + (off & ~3) + 16 * k.lane);
-    const int4 x0 = p[0], x1 = p[1], x2 = p[2], x3 = p[3], x4 = p[4];
-    int s0, s1, s2, s3;
-    if (r == 0) {
-      s0 = (x0.x + x0.y) + (x0.z + x0.w); s1 = (x1.x + x1.y) + (x1.z + x1.w);
-      s2 = (x2.x + x2.y) + (x2.z + x2.w); s3 = (x3.x + x3.y) + (x3.z + x3.w);
-    } else if (r == 1) {
-      s0 = (x0.y + x0.z) + (x0.w + x1.x); s1 = (x1.y + x1.z) + (x1.w + x2.x);
-      s2 = (x2.y + x2.z) + (x2.w + x3.x); s3 = (x3.y + x3.z) + (x3.w + x4.x);
-    } else if (r == 2) {
-      s0 = (x0.z + x0.w) + (x1.x + x1.y); s1 = (x1.z + x1.w) + (x2.x + x2.y);
-      s2 = (x2.z + x2.w) + (x3.x + x3.y); s3 = (x3.z + x3.w) + (x4.x + x4.y);
-    } else {
-      s0 = (x0.w + x1.x) + (x1.y + x1.z); s1 = (x1.w + x2.x) + (x2.y + x2.z);
-      s2 = (x2.w + x3.x) + (x3.y + x3.z); s3 = (x3.w + x4.x) + (x4.y + x4.z);
+    const int4* p = reinterpret_cast<const int4*>(k.win() + (off & ~3)) + k.lane;
+    const int4 x0 = p[0], x1 = p[32], x2 = p[64], x3 = p[96];
+    int lo[4], hi[4];
+    const int4 xs[4] = {x0, x1, x2, x3};
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int s01 = xs[q].x + xs[q].y;
+      const int l = r == 0 ? 0 : r == 1 ? xs[q].x : r == 2 ? s01 : s01 + xs[q].z;
+      lo[q] = l;
+      hi[q] = (s01 + (xs[q].z + xs[q].w)) - l;
     }
-    int4 o;
-    o.x = (s0 + ((s0 >> 31) & 3)) >> 2;
-    o.y = (s1 + ((s1 >> 31) & 3)) >> 2;
-    o.z = (s2 + ((s2 >> 31) & 3)) >> 2;
-    o.w = (s3 + ((s3 >> 31) & 3)) >> 2;
-    // 128 values: the few past maxRequired / 4 only ever meet masked samples
-    reinterpret_cast<int4*>(k.ds())[k.lane] = o;
+    const int nb = (k.lane + 1) & 31;
+    int t[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) t[q] = __shfl_sync(kFull, lo[q], nb);
+    const bool last = k.lane == 31;  // its neighbour is lane 0 of the next round of vectors
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      // (value 127 would need vector 128: it only ever meets masked samples)
+      const int s = hi[q] + (last ? (q < 3 ? t[q < 3 ? q + 1 : 3] : 0) : t[q]);
+      k.ds()[32 * q + k.lane] = (s + ((s >> 31) & 3)) >> 2;
+    }
   }
   __syncwarp();
   AT_MARK(0);

@@ -96,6 +96,7 @@ __device__ __forceinline__ void stage_span(const int16_t* ptr, long long f0, int
       const int4* vp = reinterpret_cast<const int4*>(ptr + (fv0 - f0) * C);
       const int nvec = (int)(c1 - c0);
       T* d = dst + (fv0 - start);
+      const bool d_aligned = (reinterpret_cast<size_t>(d) & 15) == 0;
       short* r = raw16 ? raw16 + (fv0 - start) * C : nullptr;
       for (int vb = tid; vb < nvec; vb += 4 * THREADS) {
         int4 q4[4];
@@ -110,10 +111,22 @@ __device__ __forceinline__ void stage_span(const int16_t* ptr, long long f0, int
           if (v >= nvec) continue;
           const int w[4] = {q4[u].x, q4[u].y, q4[u].z, q4[u].w};
           if (C == 1) {
+            // 16-byte stores when the destination of a vector is 16-byte aligned (scalar stores
+            // of a widened vector are 8-way bank conflicts: lanes are 32 bytes apart)
+            if (sizeof(T) == 2 && d_aligned) {
+              *reinterpret_cast<int4*>(d + v * 8) = q4[u];
+            } else if (sizeof(T) == 4 && d_aligned) {
+              int4* d4 = reinterpret_cast<int4*>(d + v * 8);
+              d4[0] = make_int4((int)(T)(short)(w[0] & 0xffff), (int)(T)(short)(w[0] >> 16), (int)(T)(short)(w[1] & 0xffff),
+                                (int)(T)(short)(w[1] >> 16));
+              d4[1] = make_int4((int)(T)(short)(w[2] & 0xffff), (int)(T)(short)(w[2] >> 16), (int)(T)(short)(w[3] & 0xffff),
+                                (int)(T)(short)(w[3] >> 16));
+            } else {
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-              d[v * 8 + 2 * j] = (T)(short)(w[j] & 0xffff);
-              d[v * 8 + 2 * j + 1] = (T)(short)(w[j] >> 16);
+              for (int j = 0; j < 4; j++) {
+                d[v * 8 + 2 * j] = (T)(short)(w[j] & 0xffff);
+                d[v * 8 + 2 * j + 1] = (T)(short)(w[j] >> 16);
+              }
             }
           } else {
 #pragma unroll

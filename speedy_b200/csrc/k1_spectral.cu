@@ -203,11 +203,14 @@ __global__ void __launch_bounds__(WARPS * 32) k1_spectral_480(K1Params p) {
   __syncwarp();
 
   // Per-lane constants.
-  // pass 1: lane = q*15 + m2 handles the radix-8 butterfly of residue m2 of FFT q
-  const int q1 = lane / 15, m2 = lane % 15;
+  // pass 1: lane = q*16 + m2 (m2 < 15) handles the radix-8 butterfly of residue m2 of FFT q:
+  // one FFT per half-warp, so that the 8-byte stores of a half-warp stay inside one FFT's
+  // rows (no bank conflict between the two)
+  const int q1 = lane >> 4, m2 = lane & 15;
+  const bool p1_live = m2 < 15;
   float2 tw[8];  // W_240^{m2 (2 j1 + q)}
 #pragma unroll
-  for (int j1 = 0; j1 < 8; j1++) tw[j1] = p.tw_half[(m2 * (2 * j1 + q1)) % 240];
+  for (int j1 = 0; j1 < 8; j1++) tw[j1] = p.tw_half[(m2 * (2 * j1 + q1)) % 240];  // (m2 = 15: unused)
   // pass 2: lane = slot*16 + q*8 + j1 handles one radix-15 butterfly
   const int slot2 = lane >> 4, q2 = (lane >> 3) & 1, j1_2 = lane & 7;
 
@@ -230,29 +233,32 @@ __global__ void __launch_bounds__(WARPS * 32) k1_spectral_480(K1Params p) {
   // windows are processed in pairs (kk, kk+1), starting at the halo k0-1
   for (int kk = k0 - 1; kk < k1; kk += 2) {
     // ---- pass 0: int16 -> float, pre-emphasis, Hamming ---------------------
-    // eight consecutive samples per lane (30 lanes x 8 = 240): one 16-byte load of
-    // samples, two of the window table, two 16-byte stores
+    // lane l < 30 takes samples 4l .. 4l+3 and 120 + 4l .. 120 + 4l+3: 8-byte loads of
+    // samples, 16-byte loads of the window table and 16-byte stores, all at consecutive
+    // addresses across the warp (no bank conflicts)
 #pragma unroll
     for (int slot = 0; slot < 2; slot++) {
       const int k = kk + slot;
       const int o = (k - (k0 - 1)) * S16;
-      float4* v4 = reinterpret_cast<float4*>(ws.z[slot]) + 2 * lane;
+      float4* v4 = reinterpret_cast<float4*>(ws.z[slot]) + lane;
       const bool live = (k >= 0) && (k < k1);
       if (lane < 30) {
         float4 o0 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), o1 = o0;
         if (live) {
-          const short* sp = ws.samp + o + 8 * lane;
-          const int4 raw = *reinterpret_cast<const int4*>(sp);
+          const short* sp = ws.samp + o + 4 * lane;
+          const int2 ra = *reinterpret_cast<const int2*>(sp);
+          const int2 rb = *reinterpret_cast<const int2*>(sp + 120);
           // state entering sample 0 is the last sample of the previous window,
           // i.e. sample P-1 of this one (speedy.c:416-425; window k-1 ends at
           // k*S + P - 1); 0 before the first window.
           const float xm = (float)(lane > 0 ? sp[-1] : (k >= 1 ? ws.samp[o + P16 - 1] : 0));
-          const float x0 = (float)(short)(raw.x & 0xffff), x1 = (float)(raw.x >> 16);
-          const float x2 = (float)(short)(raw.y & 0xffff), x3 = (float)(raw.y >> 16);
-          const float x4 = (float)(short)(raw.z & 0xffff), x5 = (float)(raw.z >> 16);
-          const float x6 = (float)(short)(raw.w & 0xffff), x7 = (float)(raw.w >> 16);
-          const float4 w0 = *reinterpret_cast<const float4*>(s_win + 8 * lane);
-          const float4 w1 = *reinterpret_cast<const float4*>(s_win + 8 * lane + 4);
+          const float xn = (float)sp[119];
+          const float x0 = (float)(short)(ra.x & 0xffff), x1 = (float)(ra.x >> 16);
+          const float x2 = (float)(short)(ra.y & 0xffff), x3 = (float)(ra.y >> 16);
+          const float x4 = (float)(short)(rb.x & 0xffff), x5 = (float)(rb.x >> 16);
+          const float x6 = (float)(short)(rb.y & 0xffff), x7 = (float)(rb.y >> 16);
+          const float4 w0 = *reinterpret_cast<const float4*>(s_win + 4 * lane);
+          const float4 w1 = *reinterpret_cast<const float4*>(s_win + 120 + 4 * lane);
           // y = x - 0.97 * state (speedy.c:422, evaluated there in double): 0.97 is
           // split into a float and its remainder so the constant carries no error;
           // the /32768 of speedy.c:558 is folded into the window table.
@@ -260,13 +266,13 @@ __global__ void __launch_bounds__(WARPS * 32) k1_spectral_480(K1Params p) {
           o0.y = __fmul_rn(__fmaf_rn(-kPreLo, x0, __fmaf_rn(-kPreHi, x0, x1)), w0.y);
           o0.z = __fmul_rn(__fmaf_rn(-kPreLo, x1, __fmaf_rn(-kPreHi, x1, x2)), w0.z);
           o0.w = __fmul_rn(__fmaf_rn(-kPreLo, x2, __fmaf_rn(-kPreHi, x2, x3)), w0.w);
-          o1.x = __fmul_rn(__fmaf_rn(-kPreLo, x3, __fmaf_rn(-kPreHi, x3, x4)), w1.x);
+          o1.x = __fmul_rn(__fmaf_rn(-kPreLo, xn, __fmaf_rn(-kPreHi, xn, x4)), w1.x);
           o1.y = __fmul_rn(__fmaf_rn(-kPreLo, x4, __fmaf_rn(-kPreHi, x4, x5)), w1.y);
           o1.z = __fmul_rn(__fmaf_rn(-kPreLo, x5, __fmaf_rn(-kPreHi, x5, x6)), w1.z);
           o1.w = __fmul_rn(__fmaf_rn(-kPreLo, x6, __fmaf_rn(-kPreHi, x6, x7)), w1.w);
         }
         v4[0] = o0;
-        v4[1] = o1;
+        v4[30] = o1;
       }
     }
     __syncwarp();
@@ -275,13 +281,13 @@ __global__ void __launch_bounds__(WARPS * 32) k1_spectral_480(K1Params p) {
 #pragma unroll
     for (int slot = 0; slot < 2; slot++) {
       float2 a[8];
-      if (lane < 30) {
+      if (p1_live) {
         const float2* zin = ws.z[slot];
 #pragma unroll
         for (int m1 = 0; m1 < 8; m1++) a[m1] = zin[15 * m1 + m2];  // z[m] = (v[2m], v[2m+1])
       }
       __syncwarp();
-      if (lane < 30) {
+      if (p1_live) {
         if (q1) {
           // odd output bins: z[m] * W_240^m = z[m] * W_16^{m1} * W_240^{m2};
           // W_240^{m2} is folded into tw[], W_16^{m1} applied here.

@@ -76,6 +76,8 @@ namespace {
 constexpr int kPad = 32;  // over-read slack behind the window and the decimated copy
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kMaxGroups = 64;  // lag groups of four per search (>= 2 * skip + 2)
+// per-lag totals: [2][4 * kMaxGroups], or the 16 kHz search's padded rows (amdf16.cuh)
+constexpr int kSumsWords = ((2 * 4 * kMaxGroups > amdf16::kPartWords ? 2 * 4 * kMaxGroups : amdf16::kPartWords) + 3) & ~3;
 
 template <int NW, int CH, bool K16 = false>
 struct Sonic {
@@ -621,7 +623,7 @@ struct Sonic {
 __host__ __device__ inline size_t k4_stream_smem(const Geometry& g, int buf_frames) {
   size_t b = (size_t)(buf_frames + kPad) * sizeof(int);
   b += (size_t)((g.max_required / g.skip + kPad + 3) & ~3) * sizeof(int);
-  b += (size_t)2 * 4 * kMaxGroups * sizeof(unsigned);
+  b += (size_t)kSumsWords * sizeof(unsigned);
   b += (size_t)((g.max_period + 4) & ~3) * sizeof(unsigned);  // overlap-add division constants
   b += (size_t)((g.max_period + 8) & ~3) * sizeof(float);     // reciprocals of the lags (16 kHz search)
   if (g.channels > 1) b += (size_t)buf_frames * g.channels * sizeof(short) + 16;  // + one vector of over-read
@@ -663,12 +665,12 @@ __global__ void __launch_bounds__(NW * 32, MINB) k4_sonic(K4Params p) {
   k.w32 = reinterpret_cast<int*>(smem_raw);
   k.ds32 = k.w32 + k.bufN + kPad;
   k.sums = reinterpret_cast<unsigned*>(k.ds32 + ((k.maxReq / k.skip + kPad + 3) & ~3));
-  unsigned* magic_tab = k.sums + 2 * 4 * kMaxGroups;  // [(maxP + 4) & ~3]
+  unsigned* magic_tab = k.sums + kSumsWords;  // [(maxP + 4) & ~3]
   k.rcp16 = reinterpret_cast<float*>(magic_tab + ((k.maxP + 4) & ~3));
   k.buf = reinterpret_cast<short*>(k.rcp16 + ((k.maxP + 8) & ~3));
   if (K16) {
     for (int n = k.vl; n < ((k.maxP + 8) & ~3); n += Sonic<NW, CH>::VL) k.rcp16[n] = n ? __frcp_rn((float)n) : 0.f;
-    for (int n = k.vl; n < 2 * 4 * kMaxGroups; n += Sonic<NW, CH>::VL) k.sums[n] = 0u;  // rows no lane writes stay zero
+    for (int n = k.vl; n < kSumsWords; n += Sonic<NW, CH>::VL) k.sums[n] = 0u;  // rows no lane writes stay zero
   }
   // long launches: the overlap-add's division constants once, off the splice chain (a
   // double division per pitch iteration otherwise); short ones compute the few they need

@@ -106,7 +106,7 @@ __host__ __device__ constexpr SpliceLayout make_layout(int max_period, int max_r
   L.rcp = lay_take(off, ((max_period + 8) & ~3) * 4);
   L.magic = lay_take(off, ((max_period + 4) & ~3) * 4);
   L.ds = lay_take(off, (max_required / skip + 32 + 16) * 4);
-  L.part = lay_take(off, 7 * 64 * 4);  // per-lag partial sums: 4 rows (coarse) + 3 rows (fine) of 64 lags
+  L.part = lay_take(off, amdf16::kPartWords * 4);  // per-lag partial sums: 4 rows (coarse) + 3 rows (fine), amdf16.cuh
   L.win = lay_take(off, (L.rw + L.mir) * 4);
   L.raw = lay_take(off, L.rr * channels * 2);
   L.oring = lay_take(off, L.or_elems * 2);
@@ -664,7 +664,7 @@ __device__ void chain_role(const K4Params& p, const SpliceLayout& L, int s, cons
   for (int n = k.lane; n < ((k.maxP + 8) & ~3); n += 32) rcp[n] = n ? __frcp_rn((float)n) : 0.f;
   for (int i = k.lane; i < 32; i += 32) k.ds()[k.maxReq / k.skip + i] = 0;
   if (K16) {
-    for (int i = k.lane; i < 7 * 64; i += 32) k.part()[i] = 0u;
+    for (int i = k.lane; i < amdf16::kPartWords; i += 32) k.part()[i] = 0u;
   }
   {
     unsigned m = p.lane_map[k.lane];
