@@ -25,6 +25,7 @@ UNITS = [
     ("k2_tension.cu", ["--fmad=false"]),
     ("k4_sonic.cu", ["--fmad=false"]),
     ("k4_splice.cu", ["--fmad=false"]),
+    ("k4_chain16.cu", ["--fmad=false"]),
     ("batch.cu", ["--fmad=false"]),
     ("sonic_api.cpp", []),
 ]

@@ -249,14 +249,25 @@ __device__ __forceinline__ int search(const Ctx& k, const int* arr, int off, int
 // the span (consecutive 16-byte slots across the warp: no bank conflicts) and splits each at
 // the span's offset inside a vector; a value is the upper part of its vector plus the lower
 // part of the next one, which the neighbouring lane holds.
-template <class Ctx>
-__device__ __forceinline__ void decimate(const Ctx& k, int off) {
+//
+// Hook: work of the caller that does not depend on this search (the previous splice's
+// overlap-add and copy-through in k4_chain16.cu).  load() issues its shared-memory loads
+// before this function's own, finish() does its arithmetic and global stores under their
+// latency.  Neither may write shared memory.
+struct NoHook {
+  __device__ __forceinline__ void load() {}
+  __device__ __forceinline__ void finish() {}
+};
+
+template <class Ctx, class Hook>
+__device__ __forceinline__ void decimate(const Ctx& k, int off, Hook& hook) {
   AT_BEGIN();
-  __syncwarp();  // every lane is done reading the previous decimated copy
   {
     const int r = off & 3;
     const int4* p = reinterpret_cast<const int4*>(k.win() + (off & ~3)) + k.lane;
+    hook.load();
     const int4 x0 = p[0], x1 = p[32], x2 = p[64], x3 = p[96];
+    hook.finish();
     int lo[4], hi[4];
     const int4 xs[4] = {x0, x1, x2, x3};
 #pragma unroll
@@ -271,6 +282,7 @@ __device__ __forceinline__ void decimate(const Ctx& k, int off) {
 #pragma unroll
     for (int q = 0; q < 4; q++) t[q] = __shfl_sync(kFull, lo[q], nb);
     const bool last = k.lane == 31;  // its neighbour is lane 0 of the next round of vectors
+    __syncwarp();  // every lane is done reading the previous decimated copy
 #pragma unroll
     for (int q = 0; q < 4; q++) {
       // (value 127 would need vector 128: it only ever meets masked samples)
@@ -285,10 +297,10 @@ __device__ __forceinline__ void decimate(const Ctx& k, int off) {
 // findPitchPeriod at window offset `off`: coarse pass on the decimated copy (a static lane
 // assignment with more lanes for the longer lags: group q has q + 1 blocks), refinement at
 // the full rate (three lanes per lag group), previous-period rule.
-template <class Ctx>
-__device__ __forceinline__ int find_pitch_period(Ctx& k, int off) {
+template <class Ctx, class Hook>
+__device__ __forceinline__ int find_pitch_period(Ctx& k, int off, Hook& hook) {
   int minDiff = 0, maxDiff = 0;
-  decimate(k, off);
+  decimate(k, off, hook);
   int period = 4 * search<Ctx, 4, false>(k, k.ds(), 0, 10, 61, 4 * (2 + k.cGi), k.cGi >= 0, k.cSub, k.cG, nullptr, nullptr);
   int lo = period - 16, hi = period + 16;
   if (lo < 40) lo = 40;
@@ -303,6 +315,12 @@ __device__ __forceinline__ int find_pitch_period(Ctx& k, int off) {
   k.prevMinDiff = minDiff;
   k.prevPeriod = period;
   return result;
+}
+
+template <class Ctx>
+__device__ __forceinline__ int find_pitch_period(Ctx& k, int off) {
+  NoHook none;
+  return find_pitch_period(k, off, none);
 }
 
 }  // namespace amdf16

@@ -988,6 +988,20 @@ cudaError_t launch_k4(const K4Params& p0, cudaStream_t stream) {
       return launch_k4_splice(p0, stream);
     }
   }
+  // The chain shape (k4_chain16.cu: fixed overlapping windows prefetched by TMA bulk copies,
+  // output deferred into the next search) is selected with SPEEDY_K4_CHAIN=1 for 16 kHz mono
+  // writes of at least a second of audio.  Measured at 1024 x 60 s (profiles/README.md): 11.9 ms
+  // against 12.4 ms for this kernel when each runs alone, but 19.0 against 18.1 ms for the whole
+  // step, where the analysis kernels share the SMs: its extra (predicated) instructions cost more
+  // there than the latency it hides, so it is not the default.
+  {
+    const int chain = getenv("SPEEDY_K4_CHAIN") ? atoi(getenv("SPEEDY_K4_CHAIN")) : 0;
+    const bool short_launch = p0.flush || p0.frames - p0.done <= (long long)p0.g.rate;
+    const int max_streams = getenv("SPEEDY_K4_CHAIN_MAX") ? atoi(getenv("SPEEDY_K4_CHAIN_MAX")) : 148 * 8;
+    if (chain && !short_launch && p0.threads_per_stream <= 32 && p0.n_streams <= max_streams && k4_chain16_supported(p0)) {
+      return launch_k4_chain16(p0, stream);
+    }
+  }
   K4Params p = p0;
   p.buf_frames = k4_buf_frames(p.g, p.n_streams);
   // threads per stream: with few streams per SM the serial splice chain is latency

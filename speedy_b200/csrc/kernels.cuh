@@ -134,6 +134,10 @@ cudaError_t launch_k4(const K4Params& p, cudaStream_t stream);
 // the pipelined shape (k4_splice.cu): chain / filler / output warps per stream
 bool k4_splice_supported(const K4Params& p);
 cudaError_t launch_k4_splice(const K4Params& p, cudaStream_t stream);
+// the 16 kHz mono chain shape (k4_chain16.cu): one warp per stream, position-independent
+// windows prefetched by TMA bulk copies, output fused into the next search
+bool k4_chain16_supported(const K4Params& p);
+cudaError_t launch_k4_chain16(const K4Params& p, cudaStream_t stream);
 
 // ---- bookkeeping after a write: carry the input tail, advance totals ------
 struct TailParams {

@@ -70,6 +70,28 @@ def test_pipelined_kernel_equals_one_warp_kernel(rate, speed, nonlinear):
         assert np.array_equal(a[s], b[s]), (s, len(a[s]), len(b[s]))
 
 
+@pytest.mark.parametrize("speed,nonlinear,chunk", [(2.0, 1.0, None), (3.5, 1.0, 40000), (1.3, 1.0, 33333), (0.6, 1.0, 50001),
+                                                   (2.0, 0.0, 48000), (1.0, 0.0, 40008), (2.5, 0.5, 17777), (6.0, 1.0, None)])
+def test_chain_kernel_equals_one_warp_kernel(speed, nonlinear, chunk):
+    """k4_chain16.cu (SPEEDY_K4_CHAIN=1, 16 kHz mono writes of a second or more: fixed overlapping
+    windows prefetched by TMA bulk copies, output deferred into the next search) against the
+    general one-warp kernel (SPEEDY_K4_CHAIN=0): same output bytes and status for whole writes,
+    for chunks that leave the stream at frame counts that are not multiples of eight (the bulk
+    copies then fall back to plain loads) and for rows that are not 16-byte aligned."""
+    n, rate = 48, 16000
+    frames = rate * 10 + (0 if chunk is None else 123)
+    pcm = ol.synth(777, n, rate, 1, frames)
+    launches = sb.kernel_launches()
+    with _env(SPEEDY_K4_CHAIN=1):
+        a, _, st_a = gpu_process(pcm, rate, speed, nonlinear=nonlinear, taps=0, chunk=chunk)
+    with _env(SPEEDY_K4_CHAIN=0):
+        b, _, st_b = gpu_process(pcm, rate, speed, nonlinear=nonlinear, taps=0, chunk=chunk)
+    assert sb.kernel_launches() > launches
+    assert np.array_equal(st_a, st_b)
+    for s in range(n):
+        assert np.array_equal(a[s], b[s]), (s, len(a[s]), len(b[s]))
+
+
 @pytest.mark.parametrize("speed", [2.0, 0.7])
 def test_write_after_flush_linear(speed):
     """sonicFlushStream leaves the stream usable (upstream sets numInputSamples = 0): a write
