@@ -76,7 +76,22 @@ def main():
         print(name, "out frames", r["out"].shape[0],
               "tensions", len(r.get("tension", [])))
     np.savez_compressed(os.path.join(HERE, "reference_outputs.npz"), **out)
+    matlab_goldens()
     print("wrote", os.listdir(HERE))
+
+
+def matlab_goldens():
+    """The reference-held Matlab dumps of TestTapestryFeatureComputations
+    (speedy_test.cc:859-1057; test_data/tapestry_{spectrogram,normalized_spectrogram,
+    features}_data.txt): the test reads the twelve feature columns in full but only time
+    step 150 of the two spectrograms, so that is what the fixture keeps (float32, as the
+    test's ReadFloatMatrix parses them)."""
+    spec = np.loadtxt(os.path.join(REF_DATA, "tapestry_spectrogram_data.txt"), dtype=np.float32)
+    norm = np.loadtxt(os.path.join(REF_DATA, "tapestry_normalized_spectrogram_data.txt"), dtype=np.float32)
+    feat = np.loadtxt(os.path.join(REF_DATA, "tapestry_features_data.txt"), dtype=np.float32)
+    assert spec.shape == (314, 330) and norm.shape == (314, 330) and feat.shape == (314, 12)
+    np.savez_compressed(os.path.join(HERE, "matlab_tapestry.npz"), spectrogram_row150=spec[150],
+                        normalized_row150=norm[150], features=feat, shape=np.array(spec.shape, np.int32))
 
 
 if __name__ == "__main__":

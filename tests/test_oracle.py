@@ -250,6 +250,35 @@ def test_tapestry_frame_counts(golden_inputs):  # speedy_test.cc:859-941
     assert np.all(np.abs(np.array(energy[1:]) - 1) < 4e-3)
 
 
+@KISS
+def test_tapestry_feature_computations_matlab(golden_inputs):  # speedy_test.cc:859-1057
+    """The reference-held Matlab dumps, with the reference's own SNR floors and best-delay
+    table, on the compiled reference (its speedy.c over our FFT restatement): this is what
+    pins the FFT restatement and the build of oracle/_ref to values the reference owns."""
+    import matlab_checks as mc
+    pcm, rate = golden_inputs["tapestry22k"]
+    lib = ol.ref("kiss")
+    s = lib.speedyCreateStream(rate)
+    x = f32(pcm[:, 0] / 32768.0)
+    window = lib.speedyInputFrameSize(s)
+    assert window == 330 and lib.speedyFFTSize(s) == 660
+    step = np.float32(rate / np.float32(100))
+    frames = int((len(x) - window) / step + 1)
+    spec, norm, feat, n_tension = [], [], [], 0
+    for t in range(frames):
+        begin = int(np.floor(float(t * step) + 0.5))
+        lib.speedyAddData(s, ol.fptr(f32(x[begin:begin + window])), t)
+        spec.append(arr(lib.speedyGetSpectrogram(s), 330))
+        v = C.c_float()
+        if lib.speedyComputeTension(s, n_tension, C.byref(v)):
+            n_tension += 1
+            norm.append(arr(lib.speedyGetNormalizedSpectrogram(s), 330))
+            feat.append(arr(lib.speedyGetInternalState(s), 15))
+    lib.speedyDestroyStream(s)
+    got = mc.check(np.array(spec), np.array(norm), np.array(feat))
+    assert got["spectrogram_snr_db"] > 27 and got["Audio Tension"][0] == 0
+
+
 # ---- 2. the restatement against the compiled reference and the fixtures ------
 
 CASES = [("kiss", True, False), ("fftw", False, True)]
