@@ -98,6 +98,62 @@ int sonicIntWriteShortToStream(sonicStream stream, const short* inBuffer, int sa
 int sonicIntReadShortFromStream(sonicStream stream, short* outBuffer, int bufferSize);
 int sonicIntFlushStream(sonicStream stream);
 
+/* ------------------------------------------------------------------------ *
+ * 1b. Session pool: many sonicStream handles multiplexed onto ONE device batch.
+ *
+ * A libsonic client with thousands of live handles (BASELINE.json config 5: 16384 sessions
+ * fed 10 ms chunks through sonicWriteShortToStream, soniclib.c:391-452) would otherwise be
+ * thousands of batches of one.  Handles opened from a pool share one speedyBatch: a write
+ * only queues the samples in the pool's page-locked staging row of that handle; one
+ * coalesced step (one host->device copy, the four kernels over every session with pending
+ * input, one device->host read) runs when
+ *   - a handle with queued input is read, flushed or asked how much it has available,
+ *   - a handle's staging row is full,
+ *   - `auto_step_sessions` handles have queued input (0: never by count), or
+ *   - speedySessionPoolStep is called.
+ * Each session's result is bit-identical to feeding the same samples to its own stream
+ * (chunking never changes the output, tests/test_gpu_parity.py); only WHEN output becomes
+ * readable differs from the reference.  All drop-in calls of section 1 work on pooled
+ * handles except the five debug callbacks (a pooled handle ignores them: taps of thousands
+ * of sessions are what the batched API's taps are for) and sonicSetRate != 1.
+ * sonicDestroyStream closes the session and frees its slot.  Calls are serialised by a
+ * mutex per pool.  Setting the environment variable SPEEDY_B200_POOL_SESSIONS=<n> makes
+ * plain sonicCreateStream open its handles from an implicit pool of n sessions per
+ * (sample rate, channels), so an unmodified client is multiplexed too.
+ * ------------------------------------------------------------------------ */
+struct speedySessionPoolStruct;
+typedef struct speedySessionPoolStruct* speedySessionPool;
+
+typedef struct {
+  int32_t sample_rate;
+  int32_t num_channels;
+  int32_t max_sessions;        /* slots of the shared batch */
+  int32_t device;
+  int32_t max_pending_frames;  /* staging row per session; default 100 ms of audio */
+  float min_speed;             /* sizes the per-step output room (frames / min_speed); default 0.25 */
+  int32_t auto_step_sessions;  /* step as soon as this many sessions have queued input; 0 = off */
+} speedySessionPoolConfig;
+
+typedef struct {
+  int64_t steps;            /* coalesced steps run so far */
+  int64_t session_writes;   /* sonicWrite* calls absorbed */
+  int64_t sessions_served;  /* sum over steps of sessions that had input */
+  int32_t open_sessions;
+  int32_t pending_sessions; /* sessions with queued input right now */
+  double last_step_ms;      /* host wall time of the last step */
+} speedySessionPoolStats;
+
+void speedySessionPoolDefaultConfig(speedySessionPoolConfig* cfg);
+/* NULL on failure (speedyBatchLastError()). */
+speedySessionPool speedySessionPoolCreate(const speedySessionPoolConfig* cfg);
+/* Closes every handle still open, then frees the batch. */
+void speedySessionPoolDestroy(speedySessionPool pool);
+/* A new session (library defaults: speed 1, linear, feedback 0.1); NULL when the pool is full. */
+sonicStream speedySessionPoolOpen(speedySessionPool pool);
+/* Process everything queued now.  Returns the number of sessions served, -1 on failure. */
+int speedySessionPoolStep(speedySessionPool pool);
+int speedySessionPoolGetStats(speedySessionPool pool, speedySessionPoolStats* stats);
+
 /* ======================================================================== *
  * 2. Batched multi-stream API (new)
  * ======================================================================== */
@@ -179,6 +235,11 @@ int speedyBatchWrite(speedyBatch batch, const int16_t* h_in,
 /* sonicFlushStream for every stream (soniclib.c:529-552). */
 int speedyBatchFlushDevice(speedyBatch batch, void* cuda_stream);
 int speedyBatchFlush(speedyBatch batch);
+/* The same for the streams with a non-zero entry in the host array mask[num_streams]
+ * only; the others keep their pending input (the session pool's per-handle flush). */
+int speedyBatchFlushStreams(speedyBatch batch, const int32_t* h_mask);
+/* Back to the just-created state for the masked streams only (parameters are kept). */
+int speedyBatchResetStreams(speedyBatch batch, const int32_t* h_mask);
 
 /* Read: moves every stream's pending output (sonicReadShortFromStream drained
  * to empty) to out + s * stride_frames * num_channels and stores the number of

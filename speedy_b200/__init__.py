@@ -36,6 +36,17 @@ spectrogramFunction = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.POINTER(C.c_float
 _lib = None
 
 
+class SessionPoolConfig(C.Structure):  # speedySessionPoolConfig
+    _fields_ = [("sample_rate", C.c_int32), ("num_channels", C.c_int32), ("max_sessions", C.c_int32),
+                ("device", C.c_int32), ("max_pending_frames", C.c_int32), ("min_speed", C.c_float),
+                ("auto_step_sessions", C.c_int32)]
+
+
+class SessionPoolStats(C.Structure):  # speedySessionPoolStats
+    _fields_ = [("steps", C.c_int64), ("session_writes", C.c_int64), ("sessions_served", C.c_int64),
+                ("open_sessions", C.c_int32), ("pending_sessions", C.c_int32), ("last_step_ms", C.c_double)]
+
+
 def lib():
     """The loaded C-ABI library.  Raises if it has not been built."""
     global _lib
@@ -77,6 +88,15 @@ def lib():
         "speedyBatchSynthDevice": (C.c_int, [i16p, C.c_uint64, C.c_int32, C.c_int32, C.c_int32, C.c_int64, vp]),
         "speedyBatchHostAlloc": (C.c_void_p, [C.c_size_t, C.c_int]),
         "speedyBatchHostFree": (None, [C.c_void_p]),
+        "speedyBatchFlushStreams": (C.c_int, [vp, vp]),
+        "speedyBatchResetStreams": (C.c_int, [vp, vp]),
+        # session pool (many drop-in handles on one batch)
+        "speedySessionPoolDefaultConfig": (None, [C.POINTER(SessionPoolConfig)]),
+        "speedySessionPoolCreate": (vp, [C.POINTER(SessionPoolConfig)]),
+        "speedySessionPoolDestroy": (None, [vp]),
+        "speedySessionPoolOpen": (vp, [vp]),
+        "speedySessionPoolStep": (C.c_int, [vp]),
+        "speedySessionPoolGetStats": (C.c_int, [vp, C.POINTER(SessionPoolStats)]),
         # Sonic / Speedy drop-in
         "sonicCreateStream": (vp, [C.c_int, C.c_int]),
         "sonicDestroyStream": (None, [vp]),
@@ -327,3 +347,46 @@ def host_alloc(shape, dtype=np.int16, write_combined=False):
 def host_free(arr):
     lib().speedyBatchHostFree(arr.ctypes.data)
 
+
+
+class SessionPool:
+    """Mirror of the session pool (speedy_b200.h section 1b): handles from open() are plain
+    sonicStream handles for the drop-in calls (lib().sonicWriteShortToStream ...)."""
+
+    def __init__(self, rate, channels=1, max_sessions=1024, device=0, max_pending_frames=0, min_speed=0.25,
+                 auto_step_sessions=0):
+        cfg = SessionPoolConfig()
+        lib().speedySessionPoolDefaultConfig(C.byref(cfg))
+        cfg.sample_rate, cfg.num_channels, cfg.max_sessions, cfg.device = rate, channels, max_sessions, device
+        cfg.max_pending_frames, cfg.min_speed, cfg.auto_step_sessions = max_pending_frames, min_speed, auto_step_sessions
+        self.h = lib().speedySessionPoolCreate(C.byref(cfg))
+        if not self.h:
+            raise RuntimeError("speedySessionPoolCreate failed: " + last_error())
+
+    def open(self):
+        h = lib().speedySessionPoolOpen(self.h)
+        if not h:
+            raise RuntimeError("speedySessionPoolOpen: pool is full")
+        return h
+
+    def step(self):
+        n = lib().speedySessionPoolStep(self.h)
+        if n < 0:
+            raise RuntimeError("speedySessionPoolStep failed: " + last_error())
+        return n
+
+    def stats(self):
+        st = SessionPoolStats()
+        lib().speedySessionPoolGetStats(self.h, C.byref(st))
+        return {k: getattr(st, k) for k, _ in SessionPoolStats._fields_}
+
+    def close(self):
+        if self.h:
+            lib().speedySessionPoolDestroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

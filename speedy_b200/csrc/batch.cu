@@ -202,6 +202,32 @@ __global__ void read_finish_kernel(int n, int* pending, int* status, int* counts
   pending[s] = 0;
 }
 
+// Back to the just-created state for the streams with a non-zero mask entry (what reset_state
+// does for all of them): a slot of the session pool being handed to a new session.
+__global__ void reset_streams_kernel(int n, const int32_t* mask, StreamState s) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || mask[i] == 0) return;
+  s.total[i] = 0;
+  s.status[i] = 0;
+  s.lp_energy[i] = 2.14204f;  // speedy.c:287-292
+  s.lp_diff[i] = 123.837f;
+  s.cur_dur[i] = 0.0f;
+  s.des_dur[i] = 0.0f;
+  for (int r = 0; r < kRing; r++) {
+    s.ring_comp[(size_t)i * kRing + r] = 0.0f;
+    s.ring_energy[(size_t)i * kRing + r] = 0.0f;
+    s.ring_lsd[(size_t)i * kRing + r] = 0.0f;
+  }
+  s.sonic_head[i] = 0;
+  s.sonic_fed[i] = 0;
+  s.prev_period[i] = 0;
+  s.prev_min_diff[i] = 0;
+  s.remaining_copy[i] = 0;
+  s.out_total[i] = 0;
+  s.out_count[i] = 0;
+  s.hist_base[i] = 0;
+}
+
 __global__ void __launch_bounds__(256) synth_kernel(int16_t* out, unsigned long long first_id, int rate,
                                                     int channels, long long frames) {
   const int s = blockIdx.y;
@@ -340,6 +366,7 @@ struct speedyBatchStruct {
   int16_t* d_stage;
   long long stage_frames;
   int32_t* d_counts_stage;
+  int32_t* d_mask_stage;   // per-stream masks of FlushStreams / ResetStreams (allocated on first use)
   int32_t* h_pinned_counts;
   // speedyBatchProcess: double-buffered input chunks and the copy streams
   int pipe_ready;
@@ -490,6 +517,7 @@ speedyBatch speedyBatchCreate(const speedyBatchConfig* cfg) {
   b->d_stage = nullptr;
   b->stage_frames = 0;
   b->d_counts_stage = nullptr;
+  b->d_mask_stage = nullptr;
   b->d_override = nullptr;
   b->d_override_buf = nullptr;
   b->override_capacity = 0;
@@ -929,6 +957,48 @@ int speedyBatchFlushDevice(speedyBatch b, void* cuda_stream) {
   prof_mark(b, st, 4, true);
   CU_TRY(launch_k4(k4, st));
   prof_mark(b, st, 4, false);
+  return 1;
+}
+
+// sonicFlushStream for the streams with a non-zero mask entry only (the others keep their
+// pending input): what a session pool needs when one of its handles is flushed.
+static int upload_mask(speedyBatch b, const int32_t* h_mask, cudaStream_t st) {
+  if (!b->d_mask_stage && !dev_alloc(b, &b->d_mask_stage, (size_t)b->n)) return 0;
+  CU_TRY(cudaMemcpyAsync(b->d_mask_stage, h_mask, sizeof(int32_t) * b->n, cudaMemcpyHostToDevice, st));
+  return 1;
+}
+
+int speedyBatchFlushStreams(speedyBatch b, const int32_t* h_mask) {
+  if (!b || !h_mask) return 0;
+  CU_TRY(cudaSetDevice(b->cfg.device));
+  cudaStream_t st = b->own_stream;
+  if (!upload_mask(b, h_mask, st)) return 0;
+  K4Params k4;
+  memset(&k4, 0, sizeof(k4));
+  k4.g = b->g;
+  k4.st = b->st;
+  k4.n_streams = b->n;
+  k4.hist = b->d_hist[b->hist_cur];
+  k4.hist_stride = b->hist_stride;
+  k4.flush = 1;
+  k4.flush_mask = b->d_mask_stage;
+  k4.out = b->d_out;
+  k4.out_capacity = b->out_capacity;
+  k4.threads_per_stream = b->cfg.threads_per_stream;
+  CU_TRY(launch_k4(k4, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  return 1;
+}
+
+int speedyBatchResetStreams(speedyBatch b, const int32_t* h_mask) {
+  if (!b || !h_mask) return 0;
+  CU_TRY(cudaSetDevice(b->cfg.device));
+  cudaStream_t st = b->own_stream;
+  if (!upload_mask(b, h_mask, st)) return 0;
+  reset_streams_kernel<<<(b->n + 127) / 128, 128, 0, st>>>(b->n, b->d_mask_stage, b->st);
+  count_launch();
+  CU_TRY(cudaGetLastError());
+  CU_TRY(cudaStreamSynchronize(st));
   return 1;
 }
 

@@ -640,6 +640,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k4_sonic(K4Params p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int s = blockIdx.x;
   if (s >= p.n_streams) return;
+  if (p.flush && p.flush_mask && p.flush_mask[s] == 0) return;  // a flush of some streams only
   const Geometry& g = p.g;
 
   Sonic<NW, CH, K16> k;

@@ -121,6 +121,7 @@ struct K4Params {
   const float* speeds;           // from K2
   int speeds_stride;
   int flush;                     // 1: this launch is sonicFlushStream
+  const int32_t* flush_mask;     // flush only: streams with a zero entry are left alone (null: all)
   int16_t* out;                  // [n][out_capacity][C]
   long long out_capacity;        // sample frames per stream
   int threads_per_stream;

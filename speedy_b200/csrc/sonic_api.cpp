@@ -4,12 +4,19 @@
 // bookkeeping, the host-side output FIFO sonicRead* pops from, and the five
 // debug callbacks replayed in the reference's order (soniclib.c:297-353).
 //
-// Correct, not fast: every write is a host->device copy, four kernel launches
-// and a device->host read.  Throughput comes from speedyBatch*.
+// A handle made by sonicCreateStream owns a batch of one: correct, not fast (every write is a
+// host->device copy, four kernel launches and a device->host read).  Handles opened from a
+// session pool (speedy_b200.h section 1b) share one batch: writes queue in page-locked
+// staging rows and one coalesced step serves every session with pending input.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
+#include <map>
+#include <mutex>
+#include <utility>
 #include <vector>
 
 #include "../../include/speedy_b200.h"
@@ -26,6 +33,8 @@ struct sonicStreamStruct {
   float nonlinear;
   float feedback;
   speedyBatch batch;
+  speedySessionPool pool;  // non-null: a pooled session, `slot` of the pool's batch
+  int slot;
   int window, fft, step;
   int buffer_size;  // 0 until the first nonlinear write (soniclib.c:195, 672-680)
   bool started;
@@ -118,8 +127,182 @@ static bool replay_callbacks(sonicStream s) {
   return true;
 }
 
+
+// ---- session pool ------------------------------------------------------------
+
+struct speedySessionPoolStruct {
+  speedySessionPoolConfig cfg;
+  speedyBatch batch = nullptr;
+  int n = 0, channels = 1;
+  long long row_frames = 0;  // staging row per session
+  long long out_cap = 0;     // output room per session and step
+  std::mutex mu;
+  int16_t* h_in = nullptr;   // page-locked [n][row_frames][C]
+  int16_t* h_out = nullptr;  // page-locked [n][out_cap][C]
+  std::vector<int32_t> counts, out_counts, mask, status;
+  std::vector<float> speed, nonlinear, feedback;
+  bool params_dirty = false;
+  std::vector<sonicStream> slots;  // null: free
+  std::vector<int> free_slots;
+  std::vector<char> needs_reset;   // the slot's device state is a closed session's
+  int pending = 0;                 // sessions with queued input
+  speedySessionPoolStats stats = {};
+};
+
+namespace {
+
+bool pool_push_params(speedySessionPool p) {
+  if (!p->params_dirty) return true;
+  p->params_dirty = false;
+  return speedyBatchSetSpeed(p->batch, p->speed.data(), 0.0f) &&
+         speedyBatchSetNonlinear(p->batch, p->nonlinear.data(), 0.0f) &&
+         speedyBatchSetFeedback(p->batch, p->feedback.data(), 0.0f);
+}
+
+// move what the batch produced into the sessions' FIFOs
+bool pool_collect(speedySessionPool p) {
+  if (!speedyBatchRead(p->batch, p->h_out, p->out_cap, p->out_counts.data())) return false;
+  bool full = false;
+  for (int i = 0; i < p->n; i++) {
+    const int32_t c = p->out_counts[i];
+    if (c <= 0) continue;
+    sonicStream h = p->slots[i];
+    if (h) {
+      const short* src = p->h_out + (size_t)i * p->out_cap * p->channels;
+      h->fifo.insert(h->fifo.end(), src, src + (size_t)c * p->channels);
+    }
+    if (c >= p->out_cap) full = true;
+  }
+  if (full) {
+    // a row that came back full may have lost output (min_speed too optimistic)
+    if (!speedyBatchGetStatus(p->batch, p->status.data())) return false;
+    for (int i = 0; i < p->n; i++) {
+      if (p->status[i] & (SPEEDY_STATUS_OUTPUT_OVERFLOW | SPEEDY_STATUS_READ_TRUNCATED)) return false;
+    }
+  }
+  return true;
+}
+
+// one coalesced step over every session with queued input (mutex held); sessions served or -1
+int pool_step(speedySessionPool p) {
+  if (p->pending == 0) return 0;
+  const auto t0 = std::chrono::steady_clock::now();
+  if (!pool_push_params(p)) return -1;
+  int32_t most = 0;
+  for (int i = 0; i < p->n; i++) most = std::max(most, p->counts[i]);
+  if (!speedyBatchWrite(p->batch, p->h_in, p->row_frames, most, p->counts.data())) return -1;
+  if (!pool_collect(p)) return -1;
+  const int served = p->pending;
+  std::fill(p->counts.begin(), p->counts.end(), 0);
+  p->pending = 0;
+  p->stats.steps++;
+  p->stats.sessions_served += served;
+  p->stats.last_step_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  return served;
+}
+
+bool pool_step_if_pending(sonicStream s) {
+  speedySessionPool p = s->pool;
+  return p->counts[s->slot] == 0 || pool_step(p) >= 0;
+}
+
+bool pool_reset_slot(speedySessionPool p, int slot) {
+  std::fill(p->mask.begin(), p->mask.end(), 0);
+  p->mask[slot] = 1;
+  return speedyBatchResetStreams(p->batch, p->mask.data()) != 0;
+}
+
+int pool_write(sonicStream s, const short* in, int count) {
+  speedySessionPool p = s->pool;
+  std::lock_guard<std::mutex> lock(p->mu);
+  if (s->rate != 1.0f) return 0;  // playback-rate conversion is not on this path
+  s->started = true;
+  // (the same rule as a private handle: a flushed session that switches between the linear
+  // short circuit and Speedy starts Speedy's clock at zero, soniclib.c:397-399)
+  const int mode = s->nonlinear != 0.0f ? 1 : 0;
+  if (s->last_mode >= 0 && s->last_mode != mode && s->flushed) {
+    if (!pool_step_if_pending(s) || !pool_reset_slot(p, s->slot)) return 0;
+  }
+  s->last_mode = mode;
+  s->flushed = false;
+  if (mode && s->buffer_size == 0) s->buffer_size = s->step;
+  p->stats.session_writes++;
+  for (int done = 0; done < count;) {
+    if (p->counts[s->slot] == p->row_frames && pool_step(p) < 0) return 0;
+    int32_t& have = p->counts[s->slot];
+    const int n = (int)std::min<long long>(count - done, p->row_frames - have);
+    memcpy(p->h_in + ((size_t)s->slot * p->row_frames + have) * p->channels, in + (size_t)done * p->channels,
+           (size_t)n * p->channels * sizeof(short));
+    if (have == 0) p->pending++;
+    have += n;
+    done += n;
+  }
+  if (p->cfg.auto_step_sessions > 0 && p->pending >= p->cfg.auto_step_sessions && pool_step(p) < 0) return 0;
+  return 1;
+}
+
+int pool_flush(sonicStream s) {
+  speedySessionPool p = s->pool;
+  std::lock_guard<std::mutex> lock(p->mu);
+  if (pool_step(p) < 0) return 0;  // everything queued goes first, so that the read below is this flush's only
+  if (!pool_push_params(p)) return 0;
+  std::fill(p->mask.begin(), p->mask.end(), 0);
+  p->mask[s->slot] = 1;
+  if (!speedyBatchFlushStreams(p->batch, p->mask.data())) return 0;
+  s->flushed = true;
+  return pool_collect(p) ? 1 : 0;
+}
+
+void pool_set_param(sonicStream s, std::vector<float> speedySessionPoolStruct::*field, float value) {
+  speedySessionPool p = s->pool;
+  std::lock_guard<std::mutex> lock(p->mu);
+  if ((p->*field)[s->slot] == value) return;
+  pool_step_if_pending(s);  // queued samples are processed under the parameters they were written with
+  (p->*field)[s->slot] = value;
+  p->params_dirty = true;
+}
+
+void pool_close(sonicStream s) {
+  speedySessionPool p = s->pool;
+  std::lock_guard<std::mutex> lock(p->mu);
+  if (p->counts[s->slot] > 0) {  // queued input of a closed session is dropped, as the reference's destroy does
+    p->counts[s->slot] = 0;
+    p->pending--;
+  }
+  p->slots[s->slot] = nullptr;
+  p->needs_reset[s->slot] = 1;
+  p->free_slots.push_back(s->slot);
+  p->stats.open_sessions--;
+}
+
+// SPEEDY_B200_POOL_SESSIONS=<n>: sonicCreateStream opens from an implicit pool per (rate, channels)
+std::mutex g_implicit_mu;
+std::map<std::pair<int, int>, speedySessionPool> g_implicit_pools;
+
+sonicStream implicit_pool_open(int rate, int channels) {
+  const char* e = getenv("SPEEDY_B200_POOL_SESSIONS");
+  const int n = e ? atoi(e) : 0;
+  if (n <= 0) return nullptr;
+  std::lock_guard<std::mutex> lock(g_implicit_mu);
+  speedySessionPool& p = g_implicit_pools[{rate, channels}];
+  if (!p) {
+    speedySessionPoolConfig cfg;
+    speedySessionPoolDefaultConfig(&cfg);
+    cfg.sample_rate = rate;
+    cfg.num_channels = channels;
+    cfg.max_sessions = n;
+    if (const char* d = getenv("SPEEDY_B200_POOL_DEVICE")) cfg.device = atoi(d);
+    p = speedySessionPoolCreate(&cfg);
+    if (!p) return nullptr;
+  }
+  return speedySessionPoolOpen(p);  // null when full: the caller falls back to a private batch
+}
+
+}  // namespace
+
 static int write_frames(sonicStream s, const short* in, int count) {
   if (!s) return 0;
+  if (s->pool) return pool_write(s, in, count);
   if (s->rate != 1.0f) return 0;  // playback-rate conversion is not on this path
   if (!ensure_batch(s)) return 0;
   s->started = true;
@@ -150,9 +333,23 @@ static int write_frames(sonicStream s, const short* in, int count) {
 
 extern "C" {
 
+static sonicStream new_handle(int sampleRate, int numChannels);
+
 sonicStream sonicCreateStream(int sampleRate, int numChannels) {
   if (sampleRate < 800 || numChannels < 1) return nullptr;
+  if (sonicStream pooled = implicit_pool_open(sampleRate, numChannels)) return pooled;
+  sonicStream s = new_handle(sampleRate, numChannels);
+  if (!ensure_batch(s)) {  // fails without a CUDA device: there is no CPU fallback
+    delete s;
+    return nullptr;
+  }
+  return s;
+}
+
+static sonicStream new_handle(int sampleRate, int numChannels) {
   sonicStream s = new sonicStreamStruct();
+  s->pool = nullptr;
+  s->slot = -1;
   s->sample_rate = sampleRate;
   s->channels = numChannels;
   s->speed = 1.0f;      // soniclib.c:114
@@ -175,17 +372,120 @@ sonicStream sonicCreateStream(int sampleRate, int numChannels) {
   speedyBatchFrameGeometry(sampleRate, &s->window, &s->fft, &s->step);
   s->spec_ring.resize(32);
   s->normalized.assign(s->fft, 0.0f);
-  if (!ensure_batch(s)) {  // fails without a CUDA device: there is no CPU fallback
-    delete s;
-    return nullptr;
-  }
   return s;
 }
 
 void sonicDestroyStream(sonicStream s) {
   if (!s) return;
-  speedyBatchDestroy(s->batch);
+  if (s->pool) pool_close(s);
+  else speedyBatchDestroy(s->batch);
   delete s;
+}
+
+void speedySessionPoolDefaultConfig(speedySessionPoolConfig* cfg) {
+  if (!cfg) return;
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->sample_rate = 16000;
+  cfg->num_channels = 1;
+  cfg->max_sessions = 1024;
+  cfg->device = 0;
+  cfg->max_pending_frames = 0;  // 100 ms
+  cfg->min_speed = 0.25f;
+  cfg->auto_step_sessions = 0;
+}
+
+speedySessionPool speedySessionPoolCreate(const speedySessionPoolConfig* c) {
+  if (!c || c->sample_rate < 800 || c->num_channels < 1 || c->max_sessions < 1) return nullptr;
+  speedySessionPool p = new speedySessionPoolStruct();
+  p->cfg = *c;
+  p->n = c->max_sessions;
+  p->channels = c->num_channels;
+  p->row_frames = c->max_pending_frames > 0 ? c->max_pending_frames : c->sample_rate / 10;
+  const float min_speed = c->min_speed > 0.0f ? std::max(c->min_speed, 0.01f) : 0.25f;  // speedy.c:92: speeds stop at 0.01
+  // one step can emit what it was fed plus what Sonic still held (up to 2 * maxRequired and an
+  // analysis delay of input), stretched by 1 / speed, plus a flush's padding
+  const long long max_required = 2LL * (c->sample_rate / 65);
+  p->out_cap = (long long)((double)(p->row_frames + 3 * max_required + c->sample_rate / 5) / min_speed) + 2 * max_required;
+  speedyBatchConfig cfg;
+  speedyBatchDefaultConfig(&cfg);
+  cfg.sample_rate = c->sample_rate;
+  cfg.num_channels = c->num_channels;
+  cfg.num_streams = c->max_sessions;
+  cfg.device = c->device;
+  cfg.match_matlab = 0;
+  cfg.max_write_frames = p->row_frames;
+  cfg.out_capacity = p->out_cap;
+  cfg.taps = 0;
+  p->batch = speedyBatchCreate(&cfg);
+  const size_t in_bytes = (size_t)p->n * p->row_frames * p->channels * sizeof(int16_t);
+  const size_t out_bytes = (size_t)p->n * p->out_cap * p->channels * sizeof(int16_t);
+  if (p->batch) {
+    p->h_in = (int16_t*)speedyBatchHostAlloc(in_bytes, 0);
+    p->h_out = (int16_t*)speedyBatchHostAlloc(out_bytes, 0);
+  }
+  if (!p->batch || !p->h_in || !p->h_out) {
+    speedySessionPoolDestroy(p);
+    return nullptr;
+  }
+  p->counts.assign(p->n, 0);
+  p->out_counts.assign(p->n, 0);
+  p->mask.assign(p->n, 0);
+  p->status.assign(p->n, 0);
+  p->speed.assign(p->n, 1.0f);      // soniclib.c:114
+  p->nonlinear.assign(p->n, 0.0f);  // soniclib.c:117
+  p->feedback.assign(p->n, 0.1f);   // soniclib.c:122
+  p->params_dirty = true;
+  p->slots.assign(p->n, nullptr);
+  p->needs_reset.assign(p->n, 0);
+  for (int i = p->n - 1; i >= 0; i--) p->free_slots.push_back(i);
+  return p;
+}
+
+void speedySessionPoolDestroy(speedySessionPool p) {
+  if (!p) return;
+  for (sonicStream h : p->slots) {
+    if (h) delete h;
+  }
+  if (p->h_in) speedyBatchHostFree(p->h_in);
+  if (p->h_out) speedyBatchHostFree(p->h_out);
+  speedyBatchDestroy(p->batch);
+  delete p;
+}
+
+sonicStream speedySessionPoolOpen(speedySessionPool p) {
+  if (!p) return nullptr;
+  std::lock_guard<std::mutex> lock(p->mu);
+  if (p->free_slots.empty()) return nullptr;
+  const int slot = p->free_slots.back();
+  if (p->needs_reset[slot]) {
+    if (p->counts[slot] != 0 || !pool_reset_slot(p, slot)) return nullptr;
+    p->needs_reset[slot] = 0;
+  }
+  p->free_slots.pop_back();
+  sonicStream s = new_handle(p->cfg.sample_rate, p->cfg.num_channels);
+  s->pool = p;
+  s->slot = slot;
+  p->slots[slot] = s;
+  if (p->speed[slot] != 1.0f || p->nonlinear[slot] != 0.0f || p->feedback[slot] != 0.1f) p->params_dirty = true;
+  p->speed[slot] = 1.0f;
+  p->nonlinear[slot] = 0.0f;
+  p->feedback[slot] = 0.1f;
+  p->stats.open_sessions++;
+  return s;
+}
+
+int speedySessionPoolStep(speedySessionPool p) {
+  if (!p) return -1;
+  std::lock_guard<std::mutex> lock(p->mu);
+  return pool_step(p);
+}
+
+int speedySessionPoolGetStats(speedySessionPool p, speedySessionPoolStats* stats) {
+  if (!p || !stats) return 0;
+  std::lock_guard<std::mutex> lock(p->mu);
+  *stats = p->stats;
+  stats->pending_sessions = p->pending;
+  return 1;
 }
 
 int sonicWriteShortToStream(sonicStream s, const short* inBuffer, int sampleCount) {
@@ -208,8 +508,15 @@ int sonicWriteFloatToStream(sonicStream s, const float* inBuffer, int sampleCoun
   return write_frames(s, tmp.data(), sampleCount);
 }
 
+// a pooled session with queued input is served before its FIFO is looked at
+static bool settle(sonicStream s) {
+  if (!s->pool) return true;
+  std::lock_guard<std::mutex> lock(s->pool->mu);
+  return pool_step_if_pending(s);
+}
+
 int sonicReadShortFromStream(sonicStream s, short* outBuffer, int bufferSize) {
-  if (!s || !outBuffer || bufferSize <= 0) return 0;
+  if (!s || !outBuffer || bufferSize <= 0 || !settle(s)) return 0;
   const size_t have = s->fifo.size() / s->channels;
   const size_t n = std::min(have, (size_t)bufferSize);
   if (n == 0) return 0;
@@ -219,7 +526,7 @@ int sonicReadShortFromStream(sonicStream s, short* outBuffer, int bufferSize) {
 }
 
 int sonicReadFloatFromStream(sonicStream s, float* outBuffer, int bufferSize) {
-  if (!s || !outBuffer || bufferSize <= 0) return 0;
+  if (!s || !outBuffer || bufferSize <= 0 || !settle(s)) return 0;
   const size_t have = s->fifo.size() / s->channels;
   const size_t n = std::min(have, (size_t)bufferSize);
   if (n == 0) return 0;
@@ -235,10 +542,12 @@ void sonicSetRate(sonicStream s, float rate) {
 void sonicSetSpeed(sonicStream s, float speed) {
   if (!s) return;
   s->speed = speed;
-  if (s->batch) speedyBatchSetSpeed(s->batch, nullptr, speed);
+  if (s->pool) pool_set_param(s, &speedySessionPoolStruct::speed, speed);
+  else if (s->batch) speedyBatchSetSpeed(s->batch, nullptr, speed);
 }
 
 int sonicFlushStream(sonicStream s) {
+  if (s && s->pool) return pool_flush(s);
   if (!s || !ensure_batch(s)) return 0;
   if (!speedyBatchFlush(s->batch)) return 0;
   s->flushed = true;
@@ -248,27 +557,29 @@ int sonicFlushStream(sonicStream s) {
 void sonicEnableNonlinearSpeedup(sonicStream s, float nonlinearFactor) {
   if (!s) return;
   s->nonlinear = nonlinearFactor;
-  if (s->batch) speedyBatchSetNonlinear(s->batch, nullptr, nonlinearFactor);
+  if (s->pool) pool_set_param(s, &speedySessionPoolStruct::nonlinear, nonlinearFactor);
+  else if (s->batch) speedyBatchSetNonlinear(s->batch, nullptr, nonlinearFactor);
 }
 
 void sonicSetDurationFeedbackStrength(sonicStream s, float factor) {
   if (!s) return;
   s->feedback = factor;
-  if (s->batch) speedyBatchSetFeedback(s->batch, nullptr, factor);
+  if (s->pool) pool_set_param(s, &speedySessionPoolStruct::feedback, factor);
+  else if (s->batch) speedyBatchSetFeedback(s->batch, nullptr, factor);
 }
 
 int getSonicBufferSize(sonicStream s) { return s ? s->buffer_size : 0; }
 int sonicSpectrogramSize(sonicStream s) { return s ? s->fft : 0; }
 
-void sonicTensionCallback(sonicStream s, tensionFunction fn) { if (s) s->on_tension = fn; }
+void sonicTensionCallback(sonicStream s, tensionFunction fn) { if (s && !s->pool) s->on_tension = fn; }
 tensionFunction getSonicTensionCallback(sonicStream s) { return s ? s->on_tension : nullptr; }
-void sonicSpeedCallback(sonicStream s, speedFunction fn) { if (s) s->on_speed = fn; }
+void sonicSpeedCallback(sonicStream s, speedFunction fn) { if (s && !s->pool) s->on_speed = fn; }
 speedFunction getSonicSpeedCallback(sonicStream s) { return s ? s->on_speed : nullptr; }
-void sonicFeaturesCallback(sonicStream s, featuresFunction fn) { if (s) s->on_features = fn; }
+void sonicFeaturesCallback(sonicStream s, featuresFunction fn) { if (s && !s->pool) s->on_features = fn; }
 featuresFunction getSonicFeaturesCallback(sonicStream s) { return s ? s->on_features : nullptr; }
-void sonicSpectrogramCallback(sonicStream s, spectrogramFunction fn) { if (s) s->on_spectrogram = fn; }
+void sonicSpectrogramCallback(sonicStream s, spectrogramFunction fn) { if (s && !s->pool) s->on_spectrogram = fn; }
 spectrogramFunction getSonicSpectrogramCallback(sonicStream s) { return s ? s->on_spectrogram : nullptr; }
-void sonicNormalizedSpectrogramCallback(sonicStream s, spectrogramFunction fn) { if (s) s->on_normalized = fn; }
+void sonicNormalizedSpectrogramCallback(sonicStream s, spectrogramFunction fn) { if (s && !s->pool) s->on_normalized = fn; }
 spectrogramFunction getSonicNormalizedSpectrogramCallback(sonicStream s) {
   return s ? s->on_normalized : nullptr;
 }
@@ -276,7 +587,7 @@ spectrogramFunction getSonicNormalizedSpectrogramCallback(sonicStream s) {
 int sonicIntGetNumChannels(sonicStream s) { return s ? s->channels : 0; }
 int sonicIntGetSampleRate(sonicStream s) { return s ? s->sample_rate : 0; }
 float sonicIntGetSpeed(sonicStream s) { return s ? s->speed : 0.0f; }
-int sonicIntSamplesAvailable(sonicStream s) { return s ? (int)(s->fifo.size() / s->channels) : 0; }
+int sonicIntSamplesAvailable(sonicStream s) { return s && settle(s) ? (int)(s->fifo.size() / s->channels) : 0; }
 
 // The inner Sonic stream under its SONIC_INTERNAL names (sonic2.h:22-35), as
 // sonic_test.cc:729-752 drives it: plain Sonic at the handle's speed.  Only valid while

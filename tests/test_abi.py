@@ -19,7 +19,7 @@ def declared_functions():
     names = set()
     for m in re.finditer(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\(", text):
         n = m.group(1)
-        if n.startswith(("sonic", "speedyBatch", "getSonic")):
+        if n.startswith(("sonic", "speedyBatch", "speedySessionPool", "getSonic")):
             names.add(n)
     return sorted(names)
 
