@@ -556,6 +556,21 @@ def run_cuda_streaming(args):
             out_frames += int(h_cnt.sum())
     e2e_ms = (time.perf_counter() - t_all) * 1e3 / steps
 
+    # ---- the same workload through the API BASELINE.json names: one sonicStream handle per
+    # session (pooled), sonicWriteShortToStream + sonicReadShortFromStream per 10 ms chunk ----
+    drop_in = None
+    tool = os.path.join(ROOT, "speedy_b200", "stream_bench")
+    if rank == 0 and os.path.exists(tool):
+        batch.close()
+        del d_in, d_out, h_in, h_out
+        torch.cuda.empty_cache()
+        import subprocess
+        cmd = [tool, "--sessions", str(n), "--rate", str(RATE), "--chunk", str(chunk), "--ticks", str(steps),
+               "--warmup", str(warm), "--speed", str(SPEED), "--nonlinear", str(NONLINEAR), "--feedback", str(FEEDBACK),
+               "--device", str(local)]
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+        drop_in = json.loads(r.stdout) if r.returncode == 0 else {"failed": r.stderr[-300:]}
+
     t = torch.tensor([elapsed_ms, e2e_ms], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -580,6 +595,7 @@ def run_cuda_streaming(args):
             "e2e": {"value": audio_s / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes + 4 * n,
                     "api": "speedyBatchWrite + speedyBatchRead (host chunks)"},
+            "drop_in": drop_in,
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": (in_bytes + out_bytes) / (kt[dom] / 1e3) / 1e9 if kt[dom] > 0 else 0.0,
                          "peak": peak, "unit": "GB/s",

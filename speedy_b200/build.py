@@ -75,6 +75,15 @@ def build(force=False, verbose=False):
         if verbose:
             print(" ".join(cmd))
         subprocess.run(cmd, check=True)
+    # config 5 through the drop-in API: many pooled sonicStream handles fed 10 ms chunks (host C++ only)
+    sb_src = os.path.join(HERE, "..", "tools", "stream_bench.cpp")
+    sb_tool = os.path.join(HERE, "stream_bench")
+    if os.path.exists(sb_src) and not os.environ.get("SPEEDY_B200_BUILD_OUT") and (force or _stale(sb_tool, [sb_src, OUT] + headers)):
+        cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-pthread", sb_src, "-L" + HERE, "-lspeedy_b200",
+               "-Wl,-rpath,$ORIGIN", "-o", sb_tool]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.run(cmd, check=True)
     # the evaluation tools (DTW / Teager / slopes), host C++ only
     eval_src = os.path.join(HERE, "..", "tools", "eval_tools.cpp")
     eval_lib = os.path.join(HERE, "libspeedy_eval.so")

@@ -402,10 +402,10 @@ speedySessionPool speedySessionPoolCreate(const speedySessionPoolConfig* c) {
   p->channels = c->num_channels;
   p->row_frames = c->max_pending_frames > 0 ? c->max_pending_frames : c->sample_rate / 10;
   const float min_speed = c->min_speed > 0.0f ? std::max(c->min_speed, 0.01f) : 0.25f;  // speedy.c:92: speeds stop at 0.01
-  // one step can emit what it was fed plus what Sonic still held (up to 2 * maxRequired and an
-  // analysis delay of input), stretched by 1 / speed, plus a flush's padding
+  // one step can emit what it was fed plus what Sonic's FIFO still held (it never keeps more
+  // than it needs for one search and one 10 ms buffer), stretched by 1 / speed, plus a flush's padding
   const long long max_required = 2LL * (c->sample_rate / 65);
-  p->out_cap = (long long)((double)(p->row_frames + 3 * max_required + c->sample_rate / 5) / min_speed) + 2 * max_required;
+  p->out_cap = (long long)((double)(p->row_frames + 2 * max_required + c->sample_rate / 100) / min_speed) + 2 * max_required;
   speedyBatchConfig cfg;
   speedyBatchDefaultConfig(&cfg);
   cfg.sample_rate = c->sample_rate;
