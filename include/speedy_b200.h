@@ -184,6 +184,14 @@ typedef struct {
   int64_t out_capacity;    /* per-stream output buffer, in sample frames */
   int32_t taps;            /* SPEEDY_TAP_* mask */
   int32_t threads_per_stream; /* resynthesis kernel: 0 = choose, or 32/64/128 */
+  /* White-box analysis hook (0 = off), for driving the analysis the way the reference's own
+   * tests drive speedyAddData (speedy_test.cc:859-941: explicit 330-sample frames starting at
+   * round(t * 220.5), numbered from 0): analysis frames advance by this many samples instead
+   * of rate / 100 (speedy.c:335-338) and are numbered from 0 instead of the shim's 1
+   * (soniclib.c:296).  With the window length itself, consecutive windows are disjoint and a
+   * stream that is the concatenation of explicit frames reproduces speedyAddDataShort frame by
+   * frame, pre-emphasis state included (speedy.c:416-425, 553-565). */
+  int32_t analysis_frame_step;
 } speedyBatchConfig;
 
 /* Fills cfg with the library defaults (soniclib.c:114-122: speed 1, nonlinear

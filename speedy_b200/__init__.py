@@ -25,7 +25,8 @@ class BatchConfig(C.Structure):
                 ("speed", C.c_float), ("nonlinear_factor", C.c_float),
                 ("feedback_strength", C.c_float), ("device", C.c_int32),
                 ("max_write_frames", C.c_int64), ("out_capacity", C.c_int64),
-                ("taps", C.c_int32), ("threads_per_stream", C.c_int32)]
+                ("taps", C.c_int32), ("threads_per_stream", C.c_int32),
+                ("analysis_frame_step", C.c_int32)]
 
 
 tensionFunction = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_float)
@@ -168,7 +169,8 @@ class Batch:
 
     def __init__(self, num_streams, sample_rate=16000, num_channels=1, speed=1.0,
                  nonlinear=0.0, feedback=0.1, match_matlab=False, device=0,
-                 max_write_frames=16000, out_capacity=0, taps=0, threads_per_stream=0):
+                 max_write_frames=16000, out_capacity=0, taps=0, threads_per_stream=0,
+                 analysis_frame_step=0):
         L = lib()
         cfg = BatchConfig()
         L.speedyBatchDefaultConfig(C.byref(cfg))
@@ -181,6 +183,8 @@ class Batch:
         self.n = num_streams
         self.channels = num_channels
         self.window, self.fft, self.step = frame_geometry(sample_rate)
+        if analysis_frame_step > 0:  # white-box hook (speedy_b200.h)
+            cfg.analysis_frame_step, self.step = analysis_frame_step, analysis_frame_step
         self.max_rows = max_write_frames // self.step + 2
         self.h = L.speedyBatchCreate(C.byref(cfg))
         if not self.h:

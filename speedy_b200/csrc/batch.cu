@@ -267,6 +267,7 @@ static void make_geometry(int rate, int channels, int match_matlab, Geometry* g)
   g->max_required = 2 * g->max_period;
   g->skip = rate > 4000 ? rate / 4000 : 1;       // SONIC_AMDF_FREQ
   g->hist_frames = g->max_required + (g->future + 4) * g->step + g->window + 64;
+  g->time_base = 1;  // soniclib.c:296
 }
 
 static int factorize(int n, int* f) {
@@ -448,7 +449,7 @@ int64_t speedyBatchKernelLaunches(void) { return g_launches.load(); }
 const char* speedyBatchBuildInfo(void) {
   return "speedy_b200 sm_100a: k1_spectral_480<4 warps> (radix-8 x radix-15 real FFT) | "
          "k1_spectral_mixed<128> (packed half-length Stockham FFT, any even window) | k1_spectral_bluestein<128> (chirp-z, "
-         "prime windows) | k1_spectral_generic<128> | "
+         "prime windows) | "
          "k2_tension | k4_sonic<1|2|4 warps per stream, mono specialisation> | tail | read | synth";
 }
 
@@ -532,6 +533,12 @@ speedyBatch speedyBatchCreate(const speedyBatchConfig* cfg) {
   for (int i = 0; i < kPipeEvents; i++) b->ev_pipe[i] = nullptr;
   b->d_tap_spec = b->d_tap_energy = b->d_tap_features = b->d_tap_tension = b->d_tap_speed = nullptr;
   make_geometry(cfg->sample_rate, cfg->num_channels, cfg->match_matlab, &b->g);
+  if (cfg->analysis_frame_step > 0) {  // white-box hook: explicit analysis frames (speedy_b200.h)
+    b->g.step = cfg->analysis_frame_step;
+    b->g.partial = b->g.window - (b->g.window / b->g.step) * b->g.step;
+    b->g.hist_frames = b->g.max_required + (b->g.future + 4) * b->g.step + b->g.window + 64;
+    b->g.time_base = 0;  // frames numbered as the test numbers its speedyAddData calls (speedy_test.cc:912)
+  }
   const Geometry& g = b->g;
   b->n_factors = factorize(g.fft, b->factors);
   bool ok = b->n_factors > 0;

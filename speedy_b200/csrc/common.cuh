@@ -33,6 +33,8 @@ struct Geometry {
   int max_required;  // 2 * max_period
   int skip;          // AMDF decimation
   int hist_frames;   // capacity of the carried-over input tail, sample frames
+  int time_base;     // at_time of window 0: 1 through the shim (soniclib.c:296), 0 when frames are
+                     // handed to speedyAddData directly (the white-box hook, speedy_test.cc:912)
 };
 
 // Where a kernel reads input samples: the tail carried over from earlier writes
@@ -237,7 +239,7 @@ __host__ __device__ inline int frames_analyzed(const Geometry& g, long long tota
 }
 
 __host__ __device__ inline int tensions_ready(const Geometry& g, int analyzed) {
-  int n = analyzed - g.future + 1;
+  int n = analyzed - g.future + g.time_base;
   return n > 0 ? n : 0;
 }
 

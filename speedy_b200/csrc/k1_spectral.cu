@@ -27,9 +27,7 @@
 // Any other rate: k1_spectral_mixed (even windows whose half factors into radices up
 // to 13: N = 660, 720, 960, 1440 ...: the same packed decomposition, the transforms
 // as a Stockham FFT in shared memory, one CTA per run), k1_spectral_bluestein (odd or
-// prime windows, 44.1 kHz: chirp-z on the same machinery); k1_spectral_generic is the
-// O(N R) fallback they replaced.
-#include <stdlib.h>
+// prime windows, 44.1 kHz: chirp-z on the same machinery).
 
 #include "kernels.cuh"
 
@@ -609,9 +607,11 @@ __global__ void __launch_bounds__(THREADS) k1_spectral_mixed(K1Params p) {
   src.t_old = t_old;
   src.t_new = t_new;
 
-  // Stage the run's samples (mono down-mix) once: windows k0-1 .. k1-1.
-  const long long base = (long long)(k0 - 1) * S;
-  const int need = (k1 - k0 + 1) * S + P;
+  // Stage the run's samples (mono down-mix) once: windows k0-1 .. k1-1.  With disjoint windows
+  // (P == 0, the white-box frame step) the pre-emphasis state of the first one lies before it.
+  const int lead = P == 0 ? 8 : 0;
+  const long long base = (long long)(k0 - 1) * S - lead;
+  const int need = (k1 - k0 + 1) * S + P + lead;
   stage_mono<THREADS, short>(src, base, need, t_new, samp, nullptr, tid);
   __syncthreads();
 
@@ -626,7 +626,7 @@ __global__ void __launch_bounds__(THREADS) k1_spectral_mixed(K1Params p) {
       const int k = kk + slot;
       float2 z = make_float2(0.0f, 0.0f);
       if (k >= 0 && k < k1) {
-        const int o = (k - (k0 - 1)) * S;
+        const int o = lead + (k - (k0 - 1)) * S;
         const int n = 2 * m;
         // state entering sample 0 is the last sample of the previous window, i.e.
         // sample P-1 of this one (speedy.c:416-425); 0 before the first window
@@ -843,8 +843,9 @@ __global__ void __launch_bounds__(THREADS) k1_spectral_bluestein(K1Params p) {
   src.t_old = t_old;
   src.t_new = t_new;
 
-  const long long base = (long long)(k0 - 1) * S;
-  const int need = (k1 - k0 + 1) * S + P;
+  const int lead = P == 0 ? 8 : 0;  // (disjoint windows: the first one's pre-emphasis state lies before it)
+  const long long base = (long long)(k0 - 1) * S - lead;
+  const int need = (k1 - k0 + 1) * S + P + lead;
   stage_mono<THREADS, short>(src, base, need, t_new, samp, nullptr, tid);
   __syncthreads();
 
@@ -859,7 +860,7 @@ __global__ void __launch_bounds__(THREADS) k1_spectral_bluestein(K1Params p) {
       const int k = kk + slot;
       float2 a = make_float2(0.0f, 0.0f);
       if (n < W && k >= 0 && k < k1) {
-        const int o = (k - (k0 - 1)) * S;
+        const int o = lead + (k - (k0 - 1)) * S;
         const float xm = (float)((n > 0) ? samp[o + n - 1] : (k >= 1 ? samp[o + P - 1] : 0));
         const float x0 = (float)samp[o + n];
         const float v = __fmul_rn(__fmaf_rn(-kPreLo, xm, __fmaf_rn(-kPreHi, xm, x0)), s_win[n]);
@@ -966,150 +967,6 @@ __global__ void __launch_bounds__(THREADS) k1_spectral_bluestein(K1Params p) {
 }
 
 // ---------------------------------------------------------------------------
-// Generic path: any N = 2W whose prime factors are small.  One CTA per run.
-// ---------------------------------------------------------------------------
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS) k1_spectral_generic(K1Params p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const Geometry& g = p.g;
-  const int N = g.fft, W = g.window, S = g.step, P = g.partial, half = N / 2;
-  float2* bufA = reinterpret_cast<float2*>(smem_raw);  // [N]
-  float2* bufB = bufA + N;                              // [N]
-  float* mag0 = reinterpret_cast<float*>(bufB + N);     // [half]
-  float* mag1 = mag0 + half;                            // [half]
-  float* red = mag1 + half;                             // [64]
-  __shared__ float s_e, s_mx, s_lsd;
-
-  const int tid = threadIdx.x;
-  const int lane = tid & 31, warp = tid >> 5;
-  const long long item = blockIdx.x;
-  const int s = (int)(item / p.runs_per_stream);
-  const int run = (int)(item % p.runs_per_stream);
-  if (s >= p.n_streams) return;
-
-  const Range rg = write_range(p.st.total, p.counts, p.frames, p.done, s);
-  const long long t_old = rg.t_old, t_new = rg.t_new;
-  const int kA = frames_analyzed(g, t_old);          // scratch rows count from here
-  const int kD = frames_analyzed(g, rg.t_done);      // first window of this launch
-  const int kB = frames_analyzed(g, t_new);
-  const int k0 = kD + run * kRun;
-  if (k0 >= kB) return;
-  const int k1 = min(k0 + kRun, kB);
-
-  Source src;
-  src.channels = g.channels;
-  src.hist = p.hist + (size_t)s * p.hist_stride;
-  src.in = p.in ? p.in + (size_t)s * p.in_stride_frames * g.channels : nullptr;
-  src.hist_base = p.st.hist_base[s];
-  src.t_old = t_old;
-  src.t_new = t_new;
-
-  float* cur = mag0;
-  float* last = mag1;
-  float e_last = 0.0f;
-  for (int k = k0 - 1; k < k1; k++) {
-    // window, zero-pad
-    const long long f0 = (long long)k * S;
-    for (int n = tid; n < N; n += THREADS) {
-      float out = 0.0f;
-      if (n < W && k >= 0) {
-        int xp = (n > 0) ? src.mono(f0 + n - 1) : (k >= 1 ? src.mono(f0 + P - 1) : 0);
-        int xc = src.mono(f0 + n);
-        double fc = (double)((float)xc * 3.0517578125e-05f);
-        double fp = (double)((float)xp * 3.0517578125e-05f);
-        float y = (float)__dsub_rn(fc, __dmul_rn(0.97, fp));
-        out = __fmul_rn(y, p.window[n]);
-      }
-      bufA[n] = make_float2(out, 0.0f);
-    }
-    __syncthreads();
-    // Stockham stages: y[q + s(Rp + t)] = W_n^{pt} sum_r x[q + s(p + r m)] W_R^{rt}
-    float2* x = bufA;
-    float2* y = bufB;
-    int n = N, st = 1;
-    for (int f = 0; f < p.n_factors; f++) {
-      const int R = p.factors[f];
-      const int m = n / R;
-      const int total = m * st * R;  // == N: one thread per output
-      for (int o = tid; o < total; o += THREADS) {
-        const int q = o % st;
-        const int t = (o / st) % R;
-        const int pp = o / (st * R);
-        float2 acc = make_float2(0.0f, 0.0f);
-        for (int r = 0; r < R; r++) {
-          float2 a = x[q + st * (pp + r * m)];
-          float2 w = p.tw_n[(N / R) * ((r * t) % R)];
-          acc = cadd(acc, cmul(a, w));
-        }
-        acc = cmul(acc, p.tw_n[(int)(((long long)pp * t * st) % N)]);
-        y[q + st * (R * pp + t)] = acc;
-      }
-      __syncthreads();
-      float2* tmp = x; x = y; y = tmp;
-      n = m;
-      st *= R;
-    }
-    // magnitude, energy, max
-    float e = 0.0f, mx = 0.0f;
-    for (int i = tid; i < half; i += THREADS) {
-      float2 c = x[i];
-      float mg = __fsqrt_rn(__fadd_rn(__fmul_rn(c.x, c.x), __fmul_rn(c.y, c.y)));
-      cur[i] = mg;
-      if (i >= 1) {
-        e += mg * mg;
-        mx = fmaxf(mx, mg);
-      }
-    }
-    e = warp_sum(e);
-    mx = warp_max(mx);
-    if (lane == 0) { red[warp] = e; red[32 + warp] = mx; }
-    __syncthreads();
-    if (tid == 0) {
-      float es = 0.0f, ms = 0.0f;
-      for (int w = 0; w < THREADS / 32; w++) { es += red[w]; ms = fmaxf(ms, red[32 + w]); }
-      s_e = es; s_mx = ms;
-    }
-    __syncthreads();
-    const float e_cur = s_e, mx_cur = s_mx;
-    if (k >= k0) {
-      // spectral difference: every warp takes a slice of the bins
-      const float eps = 2.2204e-16f;
-      const float inv_c = inverse_norm(e_cur), inv_l = inverse_norm(e_last);
-      const float thr = (float)((double)mx_cur / 100.0);
-      float acc = 0.0f;
-      for (int i = 1 + tid; i < half; i += THREADS) {
-        float c = cur[i], l = last[i];
-        if (c > thr && l > thr) {
-          float ratio = __fdiv_rn(__fadd_rn(__fmul_rn(c, inv_c), eps), __fadd_rn(__fmul_rn(l, inv_l), eps));
-          acc += fabsf(logf(ratio));
-        }
-      }
-      acc = warp_sum(acc);
-      if (lane == 0) red[warp] = acc;
-      __syncthreads();
-      if (tid == 0) {
-        float t = 0.0f;
-        for (int w = 0; w < THREADS / 32; w++) t += red[w];
-        s_lsd = t;
-      }
-      __syncthreads();
-      const int j = k - kA;
-      if (tid == 0) p.feat[(size_t)s * p.feat_stride + j] = make_float2(e_cur, s_lsd);
-      if (p.tap_spec) {
-        float* row = p.tap_spec + ((size_t)s * p.tap_stride + j) * N;
-        for (int i = tid; i < N; i += THREADS) {
-          float2 c = x[i];
-          row[i] = __fsqrt_rn(__fadd_rn(__fmul_rn(c.x, c.x), __fmul_rn(c.y, c.y)));
-        }
-      }
-    }
-    __syncthreads();
-    e_last = e_cur;
-    float* tmp = cur; cur = last; last = tmp;
-  }
-}
-
-// ---------------------------------------------------------------------------
 // Host-side launch
 // ---------------------------------------------------------------------------
 size_t k1_smem_bytes_480(int warps) {
@@ -1121,7 +978,7 @@ cudaError_t launch_k1(const K1Params& p, cudaStream_t stream) {
   K1Params q = p;
   q.runs_per_stream = (p.max_new_frames + kRun - 1) / kRun;
   const long long items = (long long)q.runs_per_stream * p.n_streams;
-  if (p.g.fft == 480) {
+  if (p.g.fft == 480 && p.g.step == S16 && p.g.partial == P16) {
     constexpr int WARPS = 4;
     const size_t smem = k1_smem_bytes_480(WARPS);
     static SmemOptIn opt_480;
@@ -1133,7 +990,7 @@ cudaError_t launch_k1(const K1Params& p, cudaStream_t stream) {
     const int N = p.g.fft, W = p.g.window, M = W / 2;
     // radix plan for the M-point transforms: 8, 4, 5, 3, 2, then odd primes up to 16
     int plan[kMaxFactors], np = 0, rest = M;
-    bool mixed = (W % 2 == 0) && M >= 4 && !getenv("SPEEDY_K1_GENERIC");
+    bool mixed = (W % 2 == 0) && M >= 4;
     if (mixed) {
       const int pref[] = {8, 4, 5, 3, 2, 7, 11, 13};
       for (int r : pref) {
@@ -1144,7 +1001,7 @@ cudaError_t launch_k1(const K1Params& p, cudaStream_t stream) {
       }
       mixed = rest == 1;
     }
-    if (!mixed && p.bl_L > 0 && !getenv("SPEEDY_K1_GENERIC")) {
+    if (!mixed && p.bl_L > 0) {
       // chirp-z: the plan is for the L-point transforms
       const int L = p.bl_L;
       const int pref[] = {8, 4, 5, 3, 2, 7};
@@ -1167,7 +1024,7 @@ cudaError_t launch_k1(const K1Params& p, cudaStream_t stream) {
       const int HP = (N / 2 + 3) & ~3;
       const size_t smem = (size_t)(6 * L + W + (W & 1)) * sizeof(float2) + (size_t)(((W + 3) & ~3) + 3 * HP) * sizeof(float) +
                           (THREADS / 32) * 4 * sizeof(float) +
-                          (size_t)((kRun + 1) * p.g.step + p.g.partial + 16) * sizeof(short);
+                          (size_t)((kRun + 1) * p.g.step + p.g.partial + 24) * sizeof(short);
       static SmemOptIn opt_b;
       if (cudaError_t e = opt_b.ensure(k1_spectral_bluestein<THREADS>, smem)) return e;
       k1_spectral_bluestein<THREADS><<<(unsigned)items, THREADS, smem, stream>>>(q);
@@ -1181,15 +1038,12 @@ cudaError_t launch_k1(const K1Params& p, cudaStream_t stream) {
       }
       const size_t smem = (size_t)(8 * M + 2 * M + W / 2) * sizeof(float2) + (size_t)(4 * W) * sizeof(float) +
                           (THREADS / 32) * 4 * sizeof(float) +
-                          (size_t)((kRun + 1) * p.g.step + p.g.partial + 16) * sizeof(short);
+                          (size_t)((kRun + 1) * p.g.step + p.g.partial + 24) * sizeof(short);
       static SmemOptIn opt_m;
       if (cudaError_t e = opt_m.ensure(k1_spectral_mixed<THREADS>, smem)) return e;
       k1_spectral_mixed<THREADS><<<(unsigned)items, THREADS, smem, stream>>>(q);
     } else {
-      const size_t smem = 2 * (size_t)N * sizeof(float2) + (size_t)N * sizeof(float) + 64 * sizeof(float);
-      static SmemOptIn opt_g;
-      if (cudaError_t e = opt_g.ensure(k1_spectral_generic<THREADS>, smem)) return e;
-      k1_spectral_generic<THREADS><<<(unsigned)items, THREADS, smem, stream>>>(q);
+      return cudaErrorInvalidValue;  // (speedyBatchCreate plans a chirp-z length for every window the mixed-radix kernel cannot take)
     }
   }
   count_launch();

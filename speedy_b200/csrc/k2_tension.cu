@@ -74,10 +74,10 @@ __global__ void __launch_bounds__(kWarps * 32) k2_tension(K2Params p, float alph
   // bring in the carried ring: the last kRing at_times (slot = at_time & 31)
   {
     const size_t base = (size_t)s * kRing;
-    const int a_last = kD;  // newest at_time already stored (0 = none)
+    const int a_last = kD - 1 + g.time_base;  // newest at_time already stored
     // entry for at_time t lives at ring[t & 63]; only t in (a_last-32, a_last] exist
     const int t = a_last - lane;
-    const bool ok = t >= 1;
+    const bool ok = t >= g.time_base;
     const int gslot = t & (kRing - 1);
     const float c = ok ? p.st.ring_comp[base + gslot] : 0.0f;
     const float e = ok ? p.st.ring_energy[base + gslot] : 0.0f;
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(kWarps * 32) k2_tension(K2Params p, float alph
   for (int j0 = kD - kA; j0 < kB - kA; j0 += 32) {
     const int j = j0 + lane;
     const bool have = j < kB - kA;
-    const int a = kA + j + 1;  // at_time of window kA + j (soniclib.c:296)
+    const int a = kA + j + g.time_base;  // at_time of window kA + j (soniclib.c:296: k + 1)
     const float2 ef = have ? feat[j] : make_float2(0.0f, 0.0f);
 
     // ---- energy low-pass, sequential (speedy.c:517-518) ----------------------
@@ -131,20 +131,20 @@ __global__ void __launch_bounds__(kWarps * 32) k2_tension(K2Params p, float alph
       float future_max = 0.0f, past_max = 0.0f;
       for (int i = 0; i <= F; i++) {
         const int t = r + i;
-        float v = t >= 1 ? rc[t & (kSmemRing - 1)] : 0.0f;
+        float v = t >= g.time_base ? rc[t & (kSmemRing - 1)] : 0.0f;
         v = __fmul_rn(v, __fdiv_rn((float)(F - i), (float)F));
         if (v > future_max) future_max = v;
       }
       for (int i = 0; i <= B; i++) {
         const int t = r - i;
-        float v = t >= 1 ? rc[t & (kSmemRing - 1)] : 0.0f;
+        float v = t >= g.time_base ? rc[t & (kSmemRing - 1)] : 0.0f;
         v = __fmul_rn(v, __fdiv_rn((float)(B - i), (float)B));
         if (v > past_max) past_max = v;
       }
       hyst = __fmul_rn(__fadd_rn(past_max, future_max), 0.5f);
       // speedy.c:673-703: spectrum of at_time r; at_time 0 is the all-zero row
-      e_r = r >= 1 ? re[r & (kSmemRing - 1)] : 0.0f;
-      lsd_raw = r >= 1 ? rl[r & (kSmemRing - 1)] : 0.0f;
+      e_r = r >= g.time_base ? re[r & (kSmemRing - 1)] : 0.0f;
+      lsd_raw = r >= g.time_base ? rl[r & (kSmemRing - 1)] : 0.0f;
       low = e_r <= low_thr;
     }
     const float lsd = low ? 0.0f : lsd_raw;
@@ -211,8 +211,8 @@ __global__ void __launch_bounds__(kWarps * 32) k2_tension(K2Params p, float alph
   // carry the newest kRing at_times and the recurrences to the next write
   {
     const size_t base = (size_t)s * kRing;
-    const int t = kB - lane;  // at_times kB-31 .. kB
-    if (t >= 1) {
+    const int t = kB - 1 + g.time_base - lane;  // the newest 32 at_times
+    if (t >= g.time_base) {
       p.st.ring_comp[base + (t & (kRing - 1))] = rc[t & (kSmemRing - 1)];
       p.st.ring_energy[base + (t & (kRing - 1))] = re[t & (kSmemRing - 1)];
       p.st.ring_lsd[base + (t & (kRing - 1))] = rl[t & (kSmemRing - 1)];
