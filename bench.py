@@ -109,6 +109,24 @@ def measured_peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def host_link_ceiling(world, in_bytes, out_bytes):
+    """The measured concurrent host<->device copy ceiling of this pool's boxes for `world` GPUs
+    copying at once (profiles/r02_pcie_ceiling.jsonl, made by profiles/tools/pcie_ceiling.py under
+    torchrun): the time the step's input and output volumes need on the link alone, both directions
+    busy, scaled from the volumes that run moved.  None if there is no line for this GPU count."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_pcie_ceiling.jsonl")) as f:
+            rows = [json.loads(l) for l in f if l.strip()]
+    except Exception:
+        return None
+    for r in rows:
+        if r.get("n_gpus") == world:
+            scale = (in_bytes + out_bytes) / float(r["h2d_bytes"] + r["d2h_bytes"])
+            return {"both_directions_ms": r["both_ms"] * scale, "h2d_alone_ms": r["h2d_alone_ms"] * in_bytes / r["h2d_bytes"],
+                    "aggregate_gbs": r["both_gbs_aggregate"], "source": "profiles/r02_pcie_ceiling.jsonl"}
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks and throttle reasons during the timed region.
 
@@ -421,6 +439,7 @@ def run_cuda_arm(args):
             cpu_baseline = {"value": ns * cpu_secs / dt, "unit": UNIT, "cores": cores, "kind": kind,
                             "sample": "%d of the %d streams x %d s (%.1f s of wall time on %d threads)"
                                       % (ns, n, cpu_secs, dt, cores), "build": CPU_BUILD}
+        ceiling = host_link_ceiling(world, in_bytes, out_bytes + 4 * n)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -432,7 +451,9 @@ def run_cuda_arm(args):
                        "sharding": "independent streams per rank, no collective"},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes + 4 * n,
-                    "api": "speedyBatchProcess (pinned host buffers)" + ("" if n_slabs == 1 else ", %d slabs of %d streams" % (n_slabs, slab))},
+                    "api": "speedyBatchProcess (pinned host buffers)" + ("" if n_slabs == 1 else ", %d slabs of %d streams" % (n_slabs, slab)),
+                    "host_link_ceiling": ceiling,
+                    "frac_of_host_link_ceiling": (ceiling["both_directions_ms"] / e2e_ms) if ceiling else None},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
