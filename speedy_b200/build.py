@@ -22,6 +22,7 @@ if os.environ.get("SPEEDY_K4_TIMING"):
 # the reference's C does, so they are built without FMA contraction.
 UNITS = [
     ("k1_spectral.cu", []),
+    ("k1_dft16.cu", []),
     ("k2_tension.cu", ["--fmad=false"]),
     ("k4_sonic.cu", ["--fmad=false"]),
     ("k4_splice.cu", ["--fmad=false"]),

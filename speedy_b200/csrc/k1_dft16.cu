@@ -1,0 +1,452 @@
+// K1, 16 kHz tensor-core shape — the 480-point spectrogram of speedyAddDataShort
+// (speedy.c:553-565: int16 -> float, pre-emphasis :416-425, Hamming + zero-padded FFT +
+// magnitude :438-474), frame energy (:510-523) and the raw local spectral difference
+// (:705-719) with the transform done as a GEMM on the 5th-generation tensor cores
+// (tcgen05.mma, operands in shared memory, accumulator in tensor memory).
+//
+// The DFT as a GEMM that fits one SM.  Only |X[k]| is needed, so the window can be re-centred:
+// with u = n - 119.5 (n = 0 .. 239 the pre-emphasised, Hamming-weighted samples v[n]),
+//   |X[k]| = | sum_u v(u) e^{-2 pi i k u / 480} |
+//          = | sum_{t<120} s[t] cos(th_k (t + 1/2))  -  i sum_{t<120} d[t] sin(th_k (t + 1/2)) |
+//   s[t] = v[120 + t] + v[119 - t],   d[t] = v[120 + t] - v[119 - t],   th_k = 2 pi k / 480,
+// which halves the inner dimension (K = 120 instead of 240), and because
+//   sin(th_k (t + 1/2)) = (-1)^t cos(th_{240-k} (t + 1/2))
+// the sine matrix is the cosine matrix read backwards: with d'[t] = (-1)^t d[t],
+//   Re[k] = (s . C)[k],  Im[k] = -(d' . C)[240 - k],  C[t][j] = cos(2 pi j (t + 1/2) / 480).
+// One matrix C (120 x 241, padded to 128 x 256) serves both parts, stays resident in shared memory
+// for the whole launch, and every window contributes two rows (s, d') to the M dimension.
+//
+// Precision.  fp16 operands, fp32 accumulation, each operand split into two fp16 terms: the rows at
+// the int16 scale / 4 (|s| < 2^15) as hi (top 11 bits, by truncation) + lo (the exact remainder
+// rounded to fp16), C as hi + lo: three products a_hi c_hi + a_lo c_hi + a_hi c_lo carry ~2^-21 of
+// every term, the level of an fp32 FFT of this size (tests/test_gpu_parity.py holds both to the
+// same 1e-4 bars).  The accumulator holds 2^13 X; everything downstream works on log2 |X|^2
+// differences and on the energy, rescaled exactly (powers of two).
+//
+// Shape.  One persistent CTA per SM, 8 warps.  A tile is 64 windows = 128 rows: four groups of
+// one halo window (the previous window, recomputed: its spectrum is the other operand of the
+// spectral difference) + 15 new ones, rows interleaved (2w: s, 2w + 1: d').
+//   warps 4-7  prepare the rows (16-byte global loads, pre-emphasis, window, fold, split) into
+//              the A operand (no-swizzle canonical layout: core matrices of 8 rows x 16 bytes);
+//              one elected thread issues the 24 tcgen05.mma of the tile and commits to mbarriers;
+//   warps 0-3  read the accumulator (tcgen05.ld, thread = row): lane pairs (s-row, d'-row) trade
+//              the mirrored halves by shuffle, each lane takes half of the bins: power, log2,
+//              energy, 40 dB gate, spectral difference against the window two lanes down.
+// The accumulator is double-buffered in tensor memory (2 x 256 columns), so the epilogue of tile i
+// runs under the preparation and the MMAs of tile i + 1.  Every wait is bounded (a wrong barrier
+// must not hang the device): on a time-out the kernel sets an error word and drains.
+#include <cuda_fp16.h>
+#include <math.h>
+#include <stdlib.h>
+
+#include <mutex>
+#include <vector>
+
+#include "kernels.cuh"
+
+namespace speedy {
+
+__device__ int g_k1_dft16_error;
+
+namespace {
+
+constexpr int kS = 160, kW = 240, kP = 80;
+constexpr int kGroupNew = 15, kGroups = 4, kTileNew = kGroupNew * kGroups;  // 60 new windows per tile
+constexpr int kRows = 128, kK = 128, kN = 256;
+constexpr float kPreHi = 0.97f;                          // speedy.c:422
+constexpr float kPreLo = (float)(0.97 - (double)0.97f);  // remainder of the double constant
+
+// shared memory (bytes)
+constexpr int kOffBhi = 0, kOffBlo = 65536, kOffAhi = 131072, kOffAlo = 163840;
+constexpr int kOffWin = 196608;            // float[240]: Hamming / 4
+constexpr int kOffBars = kOffWin + 1024;   // 6 mbarriers
+constexpr int kOffSlot = kOffBars + 64;    // tensor-memory base address
+constexpr int kSmemBytes = kOffSlot + 64;
+
+// element (r, k) of an [R x 128] K-major fp16 operand in the no-swizzle canonical layout: core
+// matrices of 8 rows x 16 bytes contiguous along the rows (stride byte offset 128), the 8-element
+// K chunks R * 16 bytes apart (leading byte offset)
+__host__ __device__ inline int op_off(int r, int k, int R) { return (k >> 3) * (R * 16) + (r >> 3) * 128 + (r & 7) * 16 + (k & 7) * 2; }
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t make_desc(unsigned addr, unsigned lbo_bytes, unsigned sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3fff);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version 1 (sm_100); layout type 0 = no swizzle
+  return d;
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: false (and the error word set) after about a second
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, unsigned parity) {
+  if (mbar_try(bar, parity)) return true;
+  const long long t0 = clock64();
+  while (!mbar_try(bar, parity)) {
+    if (clock64() - t0 > 2000000000LL) {
+      atomicExch(&g_k1_dft16_error, 1);
+      return false;
+    }
+  }
+  return true;
+}
+// all earlier tcgen05.mma of this thread done -> one arrival on `bar`
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_f16(unsigned tmem_d, uint64_t da, uint64_t db, unsigned idesc, unsigned accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 consecutive columns of this thread's tensor-memory lane
+__device__ __forceinline__ void tmem_ld32(unsigned taddr, float (&v)[32]) {
+  unsigned r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
+}
+
+// x = hi + lo with hi on an fp16 grid (top 11 bits, by truncation: exact) and lo the exact
+// remainder rounded to fp16; two values per call, packed as half2 bit patterns
+__device__ __forceinline__ void split2(float a, float b, unsigned& hi, unsigned& lo) {
+  const float ah = __uint_as_float(__float_as_uint(a) & 0xffffe000u), bh = __uint_as_float(__float_as_uint(b) & 0xffffe000u);
+  const __half2 h = __floats2half2_rn(ah, bh);
+  const __half2 l = __floats2half2_rn(a - ah, b - bh);
+  hi = *reinterpret_cast<const unsigned*>(&h);
+  lo = *reinterpret_cast<const unsigned*>(&l);
+}
+
+struct TileInfo {
+  int s, kt, kB, kA;  // stream, first new window of the tile, windows analysed after this launch, row base
+  bool live;
+};
+
+__device__ __forceinline__ TileInfo tile_info(const K1Params& p, int tile, int tiles_per_stream) {
+  TileInfo t;
+  t.s = tile / tiles_per_stream;
+  const int j = tile - t.s * tiles_per_stream;
+  const Range rg = write_range(p.st.total, p.counts, p.frames, p.done, t.s);
+  t.kA = frames_analyzed(p.g, rg.t_old);
+  const int kD = frames_analyzed(p.g, rg.t_done);
+  t.kB = frames_analyzed(p.g, rg.t_new);
+  t.kt = kD + j * kTileNew;
+  t.live = t.kt < t.kB && p.st.nonlinear[t.s] != 0.0f;  // soniclib.c:397-399: Speedy is bypassed in the linear mode
+  return t;
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(256, 1) k1_dft16(K1Params p, const uint4* __restrict__ dft_hi_lo, int n_tiles, int tiles_per_stream) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  float* s_win = reinterpret_cast<float*>(smem + kOffWin);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
+  uint64_t* bar_a_ready = bars + 0;   // 128 arrivals: the rows of a tile are in shared memory
+  uint64_t* bar_a_free = bars + 1;    // commit: the MMAs that read them are done
+  uint64_t* bar_acc_full = bars + 2;  // [2] commit: accumulator b holds a tile
+  uint64_t* bar_acc_free = bars + 4;  // [2] 128 arrivals: the epilogue has read accumulator b
+  unsigned* tmem_slot = reinterpret_cast<unsigned*>(smem + kOffSlot);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  // the DFT matrix (hi, then lo), already in operand layout: 128 KB, once per CTA
+  {
+    uint4* dst = reinterpret_cast<uint4*>(smem + kOffBhi);
+    for (int i = tid; i < 131072 / 16; i += 256) dst[i] = dft_hi_lo[i];
+    uint4* a = reinterpret_cast<uint4*>(smem + kOffAhi);  // rows start as zeros (the K padding stays zero)
+    for (int i = tid; i < 65536 / 16; i += 256) a[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < kW; i += 256) s_win[i] = p.window[i] * 0.25f;  // Hamming / 4: rows at the int16 scale / 4
+  }
+  if (tid == 0) {
+    mbar_init(bar_a_ready, 128);
+    mbar_init(bar_a_free, 1);
+    mbar_init(bar_acc_full + 0, 1);
+    mbar_init(bar_acc_full + 1, 1);
+    mbar_init(bar_acc_free + 0, 128);
+    mbar_init(bar_acc_free + 1, 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const unsigned tmem = *tmem_slot;
+
+  if (warp >= 4) {
+    // =========================== rows + MMA issue ===============================
+    const int ptid = tid - 128;
+    unsigned char* a_hi = smem + kOffAhi;
+    unsigned char* a_lo = smem + kOffAlo;
+    const unsigned idesc = (1u << 4) | ((unsigned)(kN >> 3) << 17) | ((unsigned)(kRows >> 4) << 24);  // f16 x f16 -> f32, K-major both
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const TileInfo ti = tile_info(p, tile, tiles_per_stream);
+      if (!ti.live) continue;
+      if (it > 0 && !mbar_wait(bar_a_free, (unsigned)(it - 1) & 1u)) break;
+      const Range rg = write_range(p.st.total, p.counts, p.frames, p.done, ti.s);
+      Source src;
+      src.channels = p.g.channels;
+      src.hist = p.hist + (size_t)ti.s * p.hist_stride;
+      src.in = p.in ? p.in + (size_t)ti.s * p.in_stride_frames * p.g.channels : nullptr;
+      src.hist_base = p.st.hist_base[ti.s];
+      src.t_old = rg.t_old;
+      src.t_new = rg.t_new;
+      // unit = (chunk of eight t, window): consecutive threads take consecutive windows
+      for (int u = ptid; u < 15 * 64; u += 128) {
+        const int c = u >> 6, w = u & 63;
+        const int g = w >> 4, wl = w & 15;
+        const int k = ti.kt + kGroupNew * g + wl - 1;  // wl = 0: the group's halo window
+        const int row = 2 * w;
+        uint4 s_hi = make_uint4(0u, 0u, 0u, 0u), s_lo = s_hi, d_hi = s_hi, d_lo = s_hi;
+        if (k >= 0 && k < ti.kB) {
+          const long long f0 = (long long)k * kS;  // first frame of the window
+          const int nu = 120 + 8 * c, nl = 112 - 8 * c;  // first sample of the upper / lower eight
+          float xu[9], xl[9];                            // [0] = the sample before
+          const int16_t* row_in = src.in ? src.in + (f0 - src.t_old) : nullptr;
+          const bool fast = src.channels == 1 && row_in != nullptr && f0 >= src.t_old && f0 + kW <= src.t_new &&
+                            (reinterpret_cast<size_t>(row_in) & 15) == 0;
+          if (fast) {
+            const uint4 qu = __ldg(reinterpret_cast<const uint4*>(row_in + nu));
+            const uint4 ql = __ldg(reinterpret_cast<const uint4*>(row_in + nl));
+            const unsigned wu[4] = {qu.x, qu.y, qu.z, qu.w}, wlw[4] = {ql.x, ql.y, ql.z, ql.w};
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+              xu[1 + 2 * i] = (float)(short)(wu[i] & 0xffffu);
+              xu[2 + 2 * i] = (float)(short)(wu[i] >> 16);
+              xl[1 + 2 * i] = (float)(short)(wlw[i] & 0xffffu);
+              xl[2 + 2 * i] = (float)(short)(wlw[i] >> 16);
+            }
+            xu[0] = (float)__ldg(row_in + nu - 1);
+            // the state entering sample 0 is the last sample of the previous window, i.e. sample
+            // P - 1 of this one (speedy.c:416-425); 0 before the first window
+            xl[0] = nl > 0 ? (float)__ldg(row_in + nl - 1) : (k >= 1 ? (float)__ldg(row_in + kP - 1) : 0.0f);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 9; i++) {
+              xu[i] = (float)src.mono(f0 + nu - 1 + i);
+              xl[i] = (nl - 1 + i >= 0) ? (float)src.mono(f0 + nl - 1 + i) : (k >= 1 ? (float)src.mono(f0 + kP - 1) : 0.0f);
+            }
+          }
+          float vu[8], vl[8];
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            // y = x - 0.97 * previous (speedy.c:422, evaluated there in double): 0.97 as a float and
+            // its remainder, so the constant carries no error
+            vu[i] = __fmul_rn(__fmaf_rn(-kPreLo, xu[i], __fmaf_rn(-kPreHi, xu[i], xu[i + 1])), s_win[nu + i]);
+            vl[i] = __fmul_rn(__fmaf_rn(-kPreLo, xl[i], __fmaf_rn(-kPreHi, xl[i], xl[i + 1])), s_win[nl + i]);
+          }
+          // t = 8c + i pairs sample 120 + t (vu[i]) with sample 119 - t (vl[7 - i])
+          float sv[8], dv[8];
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            sv[i] = vu[i] + vl[7 - i];
+            dv[i] = (i & 1) ? (vl[7 - i] - vu[i]) : (vu[i] - vl[7 - i]);  // (-1)^t d[t]
+          }
+          split2(sv[0], sv[1], s_hi.x, s_lo.x);
+          split2(sv[2], sv[3], s_hi.y, s_lo.y);
+          split2(sv[4], sv[5], s_hi.z, s_lo.z);
+          split2(sv[6], sv[7], s_hi.w, s_lo.w);
+          split2(dv[0], dv[1], d_hi.x, d_lo.x);
+          split2(dv[2], dv[3], d_hi.y, d_lo.y);
+          split2(dv[4], dv[5], d_hi.z, d_lo.z);
+          split2(dv[6], dv[7], d_hi.w, d_lo.w);
+        }
+        const int o = op_off(row, 8 * c, kRows);  // (row + 1 is the next 16 bytes)
+        *reinterpret_cast<uint4*>(a_hi + o) = s_hi;
+        *reinterpret_cast<uint4*>(a_hi + o + 16) = d_hi;
+        *reinterpret_cast<uint4*>(a_lo + o) = s_lo;
+        *reinterpret_cast<uint4*>(a_lo + o + 16) = d_lo;
+      }
+      // the tensor core reads shared memory through the async proxy
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(bar_a_ready);
+      if (ptid == 0) {
+        bool ok = mbar_wait(bar_a_ready, (unsigned)it & 1u);
+        const int b = it & 1;
+        if (ok && it >= 2) ok = mbar_wait(bar_acc_free + b, (unsigned)((it >> 1) - 1) & 1u);
+        if (ok) {
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const unsigned acc = tmem + (unsigned)(b * kN);
+          const unsigned ah = smem_u32(a_hi), al = smem_u32(a_lo);
+          const unsigned bh = smem_u32(smem + kOffBhi), bl = smem_u32(smem + kOffBlo);
+#pragma unroll 1
+          for (int ks = 0; ks < kK / 16; ks++) {  // two 8-element chunks per MMA
+            const unsigned ao = (unsigned)ks * 2u * (kRows * 16), bo = (unsigned)ks * 2u * (kN * 16);
+            const uint64_t d_ah = make_desc(ah + ao, kRows * 16, 128), d_al = make_desc(al + ao, kRows * 16, 128);
+            const uint64_t d_bh = make_desc(bh + bo, kN * 16, 128), d_bl = make_desc(bl + bo, kN * 16, 128);
+            umma_f16(acc, d_ah, d_bh, idesc, ks > 0 ? 1u : 0u);
+            umma_f16(acc, d_al, d_bh, idesc, 1u);
+            umma_f16(acc, d_ah, d_bl, idesc, 1u);
+          }
+        }
+        // (committed even after a time-out, so that the other role drains too)
+        umma_commit(bar_a_free);
+        umma_commit(bar_acc_full + b);
+      }
+      it++;
+    }
+  } else {
+    // =============================== epilogue =====================================
+    // thread = accumulator row: lane pair (2 wl, 2 wl + 1) = (s-row, d'-row) of window wl of group `warp`
+    const int role = lane & 1, wl = lane >> 1;
+    const int last_i = role ? 119 : 120;  // this lane's bins: role 0: k = i (1 .. 120), role 1: k = 240 - i (121 .. 239)
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const TileInfo ti = tile_info(p, tile, tiles_per_stream);
+      if (!ti.live) continue;
+      const int b = it & 1;
+      if (!mbar_wait(bar_acc_full + b, (unsigned)(it >> 1) & 1u)) break;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const unsigned row_base = tmem + ((unsigned)(warp * 32) << 16) + (unsigned)(b * kN);
+      const int k = ti.kt + kGroupNew * warp + wl - 1;
+      const bool out = wl >= 1 && k < ti.kB;
+      float* tap = nullptr;
+      if (p.tap_spec && out) tap = p.tap_spec + ((size_t)ti.s * p.tap_stride + (k - ti.kA)) * 480;
+      // pass 1: power and log2 power of this lane's bins; energy and peak
+      float l[128];
+      float e = 0.0f, mx = 0.0f;
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        float lo[32], hi[32];
+        tmem_ld32(row_base + 32u * c, lo);                // own columns i = 32c .. 32c + 31
+        tmem_ld32(row_base + 113u + 32u * (3 - c), hi);   // own columns 113 + m, m = 96 - 32c .. 127 - 32c
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+          const int i = 32 * c + j;
+          // the partner's column 240 - i (= 113 + (127 - i)): Re and Im of the same bin meet here
+          const float other = __shfl_xor_sync(0xffffffffu, hi[31 - j], 1);
+          const float q = __fadd_rn(__fmul_rn(lo[j], lo[j]), __fmul_rn(other, other));  // 2^26 |X|^2
+          l[i] = __log2f(q);
+          const bool counted = i >= 1 && i <= last_i;  // bins 0 and N/2 are not part of the energy
+          const float qc = counted ? q : 0.0f;
+          e += qc;
+          mx = fmaxf(mx, qc);
+          if (tap && i <= last_i) {
+            const float m = __fsqrt_rn(q) * 1.220703125e-4f;  // 2^-13
+            const int kbin = role ? 240 - i : i;
+            tap[kbin] = m;
+            if (kbin != 0 && kbin != 240) tap[480 - kbin] = m;
+          }
+        }
+      }
+      // the accumulator is in registers now: hand it back to the MMA issuer
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(bar_acc_free + b);
+      e = (e + __shfl_xor_sync(0xffffffffu, e, 1)) * 1.4901161193847656e-08f;  // 2^-26: the /32768 scale of speedy.c:558
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      // pass 2, speedy.c:705-719 in the log2 domain: with n_i = |X_i| / (sqrt(E) + eps),
+      //   log(n_c / n_l) = ln2 * (0.5 (lp_c - lp_l) + (linv_c - linv_l)),  lp = log2 |X|^2, linv = -log2(sqrt(E) + eps);
+      //   |X_i| > max|X| / 100  <=>  lp_i > log2(max p) - log2(1e4)
+      const float linv = -__log2f(__fsqrt_rn(e) + 2.2204e-16f);
+      const float linv_last = __shfl_up_sync(0xffffffffu, linv, 2);
+      const float thr = __log2f(mx) - 13.287712379549449f;
+      const float d2 = 2.0f * (linv - linv_last);
+      float acc = 0.0f;
+#pragma unroll
+      for (int i = 1; i <= 120; i++) {
+        const float ll = __shfl_up_sync(0xffffffffu, l[i], 2);  // the same bin of the previous window
+        if (i <= last_i && l[i] > thr && ll > thr) acc += fabsf((l[i] - ll) + d2);
+      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      if (out && role == 0) p.feat[(size_t)ti.s * p.feat_stride + (k - ti.kA)] = make_float2(e, acc * 0.34657359027997264f);  // ln2 / 2
+      it++;
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
+// ---- host side -------------------------------------------------------------------
+
+bool k1_dft16_supported(const K1Params& p) {
+  const Geometry& g = p.g;
+  return g.fft == 480 && g.window == kW && g.step == kS && g.partial == kP && g.channels == 1;
+}
+
+// C[t][j] = cos(2 pi j (t + 1/2) / 480) as fp16 hi + lo in operand layout (row = j, K = t), per device
+static const uint4* dft_matrix(cudaError_t* err) {
+  static std::mutex mu;
+  static const uint4* table[kMaxDevices];
+  int dev = 0;
+  if ((*err = cudaGetDevice(&dev)) != cudaSuccess) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  if (dev < 0 || dev >= kMaxDevices) {
+    *err = cudaErrorInvalidDevice;
+    return nullptr;
+  }
+  if (table[dev]) return table[dev];
+  std::vector<unsigned char> host(131072, 0);
+  for (int j = 0; j <= 240; j++) {
+    for (int t = 0; t < 120; t++) {
+      const double c = cos(2.0 * M_PI * (double)j * ((double)t + 0.5) / 480.0);
+      const __half hi = __float2half_rn((float)c);
+      const __half lo = __float2half_rn((float)(c - (double)__half2float(hi)));
+      *reinterpret_cast<__half*>(host.data() + op_off(j, t, kN)) = hi;
+      *reinterpret_cast<__half*>(host.data() + 65536 + op_off(j, t, kN)) = lo;
+    }
+  }
+  void* d = nullptr;
+  if ((*err = cudaMalloc(&d, host.size())) != cudaSuccess) return nullptr;
+  if ((*err = cudaMemcpy(d, host.data(), host.size(), cudaMemcpyHostToDevice)) != cudaSuccess) return nullptr;
+  table[dev] = reinterpret_cast<const uint4*>(d);
+  return table[dev];
+}
+
+cudaError_t launch_k1_dft16(const K1Params& p, cudaStream_t stream) {
+  cudaError_t e = cudaSuccess;
+  const uint4* dft = dft_matrix(&e);
+  if (!dft) return e;
+  static SmemOptIn opt;
+  if ((e = opt.ensure(k1_dft16, kSmemBytes)) != cudaSuccess) return e;
+  static int sms[kMaxDevices];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < kMaxDevices && sms[dev] == 0) cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+  const int n_sm = (dev >= 0 && dev < kMaxDevices && sms[dev] > 0) ? sms[dev] : 148;
+  const int tiles_per_stream = (p.max_new_frames + kTileNew - 1) / kTileNew;
+  const long long n_tiles = (long long)tiles_per_stream * p.n_streams;
+  const int grid = (int)(n_tiles < n_sm ? n_tiles : n_sm);
+  k1_dft16<<<grid, 256, kSmemBytes, stream>>>(p, dft, (int)n_tiles, tiles_per_stream);
+  count_launch();
+  return cudaGetLastError();
+}
+
+}  // namespace speedy
+
+extern "C" int speedyDebugK1Dft16Error(void) {
+  int v = 0;
+  cudaMemcpyFromSymbol(&v, speedy::g_k1_dft16_error, sizeof(v));
+  return v;
+}

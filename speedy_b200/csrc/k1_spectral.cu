@@ -29,6 +29,8 @@
 // as a Stockham FFT in shared memory, one CTA per run), k1_spectral_bluestein (odd or
 // prime windows, 44.1 kHz: chirp-z on the same machinery).
 
+#include <stdlib.h>
+
 #include "kernels.cuh"
 
 namespace speedy {
@@ -975,6 +977,12 @@ size_t k1_smem_bytes_480(int warps) {
 
 cudaError_t launch_k1(const K1Params& p, cudaStream_t stream) {
   if (p.max_new_frames <= 0) return cudaSuccess;
+  // 16 kHz mono writes of a second or more: the tensor-core shape (k1_dft16.cu), SPEEDY_K1_TC=0 turns it off
+  {
+    const char* e = getenv("SPEEDY_K1_TC");
+    const int on = e ? atoi(e) : 0;
+    if (on && p.frames - p.done >= (long long)p.g.rate && k1_dft16_supported(p)) return launch_k1_dft16(p, stream);
+  }
   K1Params q = p;
   q.runs_per_stream = (p.max_new_frames + kRun - 1) / kRun;
   const long long items = (long long)q.runs_per_stream * p.n_streams;
