@@ -26,7 +26,9 @@
 // Shape.  One persistent CTA per SM, 8 warps.  A tile is 64 windows = 128 rows: four groups of
 // one halo window (the previous window, recomputed: its spectrum is the other operand of the
 // spectral difference) + 15 new ones, rows interleaved (2w: s, 2w + 1: d').
-//   warps 4-7  prepare the rows (16-byte global loads, pre-emphasis, window, fold, split) into
+//   warps 4-7  prepare the rows: the tile's samples arrive in shared memory as one TMA bulk copy
+//              (cp.async.bulk + mbarrier, issued a tile ahead; tiles that touch the carried history
+//              are staged by the warps themselves), then pre-emphasis, window, fold and split into
 //              the A operand (no-swizzle canonical layout: core matrices of 8 rows x 16 bytes);
 //              one elected thread issues the 24 tcgen05.mma of the tile and commits to mbarriers;
 //   warps 0-3  read the accumulator (tcgen05.ld, thread = row): lane pairs (s-row, d'-row) trade
@@ -59,9 +61,11 @@ constexpr float kPreLo = (float)(0.97 - (double)0.97f);  // remainder of the dou
 // shared memory (bytes)
 constexpr int kOffBhi = 0, kOffBlo = 65536, kOffAhi = 131072, kOffAlo = 163840;
 constexpr int kOffWin = 196608;            // float[240]: Hamming / 4
-constexpr int kOffBars = kOffWin + 1024;   // 6 mbarriers
+constexpr int kOffBars = kOffWin + 1024;   // 7 mbarriers
 constexpr int kOffSlot = kOffBars + 64;    // tensor-memory base address
-constexpr int kSmemBytes = kOffSlot + 64;
+constexpr int kOffSamp = kOffSlot + 64;    // short[kTileSamples]: the tile's samples (windows kt-1 .. kt+59)
+constexpr int kTileSamples = kTileNew * kS + kW;  // 9840 samples = 19680 bytes
+constexpr int kSmemBytes = kOffSamp + kTileSamples * 2 + 32;
 
 // element (r, k) of an [R x 128] K-major fp16 operand in the no-swizzle canonical layout: core
 // matrices of 8 rows x 16 bytes contiguous along the rows (stride byte offset 128), the 8-element
@@ -94,17 +98,32 @@ __device__ __forceinline__ bool mbar_try(uint64_t* bar, unsigned parity) {
       : "memory");
   return ok != 0;
 }
-// bounded wait: false (and the error word set) after about a second
+// bounded wait (a wrong barrier must not hang the device): the try sleeps in the barrier unit
+// for up to the hinted time; false (and the error word set) after a few thousand tries
+__device__ __forceinline__ bool mbar_try_hint(uint64_t* bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(200000u)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, unsigned parity) {
   if (mbar_try(bar, parity)) return true;
-  const long long t0 = clock64();
-  while (!mbar_try(bar, parity)) {
-    if (clock64() - t0 > 2000000000LL) {
-      atomicExch(&g_k1_dft16_error, 1);
-      return false;
-    }
+#pragma unroll 1
+  for (int tries = 0; tries < 20000; tries++) {
+    if (mbar_try_hint(bar, parity)) return true;
   }
-  return true;
+  atomicExch(&g_k1_dft16_error, 1);
+  return false;
+}
+// global -> shared bulk copy (TMA, 1-D), completion counted in bytes on `bar`
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
 }
 // all earlier tcgen05.mma of this thread done -> one arrival on `bar`
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -146,25 +165,53 @@ __device__ __forceinline__ void split2(float a, float b, unsigned& hi, unsigned&
 }
 
 struct TileInfo {
-  int s, kt, kB, kA;  // stream, first new window of the tile, windows analysed after this launch, row base
-  bool live;
+  int tile, s, kt, kB, kA;  // tile id, stream, first new window, windows analysed after this launch, row base
+  const int16_t* bulk;      // rows only: the tile's samples as one aligned span of the caller's buffer, or null
 };
 
-__device__ __forceinline__ TileInfo tile_info(const K1Params& p, int tile, int tiles_per_stream) {
+// The next tile of this CTA (id >= `tile`, stride gridDim.x) that has windows to analyse; .tile >= n_tiles: none.
+// Lane 0 works it out (64-bit divisions) and the warp shares it.
+template <bool ROWS>
+__device__ __forceinline__ TileInfo next_tile(const K1Params& p, int tile, int n_tiles, int tiles_per_stream, int lane) {
   TileInfo t;
-  t.s = tile / tiles_per_stream;
-  const int j = tile - t.s * tiles_per_stream;
-  const Range rg = write_range(p.st.total, p.counts, p.frames, p.done, t.s);
-  t.kA = frames_analyzed(p.g, rg.t_old);
-  const int kD = frames_analyzed(p.g, rg.t_done);
-  t.kB = frames_analyzed(p.g, rg.t_new);
-  t.kt = kD + j * kTileNew;
-  t.live = t.kt < t.kB && p.st.nonlinear[t.s] != 0.0f;  // soniclib.c:397-399: Speedy is bypassed in the linear mode
-  return t;
+  t.bulk = nullptr;
+  for (;; tile += gridDim.x) {
+    t.tile = tile;
+    if (tile >= n_tiles) return t;
+    t.s = tile / tiles_per_stream;
+    int kt = 0, kB = 0, kA = 0, live = 0;
+    unsigned long long bulk = 0ULL;
+    if (lane == 0) {
+      const int j = tile - t.s * tiles_per_stream;
+      const Range rg = write_range(p.st.total, p.counts, p.frames, p.done, t.s);
+      kA = frames_analyzed(p.g, rg.t_old);
+      const int kD = frames_analyzed(p.g, rg.t_done);
+      kB = frames_analyzed(p.g, rg.t_new);
+      kt = kD + j * kTileNew;
+      live = kt < kB && p.st.nonlinear[t.s] != 0.0f;  // soniclib.c:397-399: Speedy is bypassed in the linear mode
+      if (ROWS && live && p.g.channels == 1 && p.in != nullptr) {
+        // frames [(kt - 1) S, (kt + 59) S + W) straight from the caller's buffer?  (Not the first
+        // tile of a write: its halo window reaches into the carried history.)
+        const long long f0 = (long long)(kt - 1) * kS;
+        if (f0 >= rg.t_old && f0 + kTileSamples <= rg.t_new) {
+          const int16_t* src = p.in + (size_t)t.s * p.in_stride_frames + (f0 - rg.t_old);
+          if ((reinterpret_cast<size_t>(src) & 15) == 0) bulk = reinterpret_cast<unsigned long long>(src);
+        }
+      }
+    }
+    live = __shfl_sync(0xffffffffu, live, 0);
+    if (!live) continue;
+    t.kt = __shfl_sync(0xffffffffu, kt, 0);
+    t.kB = __shfl_sync(0xffffffffu, kB, 0);
+    t.kA = __shfl_sync(0xffffffffu, kA, 0);
+    if (ROWS) t.bulk = reinterpret_cast<const int16_t*>(__shfl_sync(0xffffffffu, bulk, 0));
+    return t;
+  }
 }
 
 }  // namespace
 
+template <bool TAP>
 __global__ void __launch_bounds__(256, 1) k1_dft16(K1Params p, const uint4* __restrict__ dft_hi_lo, int n_tiles, int tiles_per_stream) {
   extern __shared__ __align__(1024) unsigned char smem[];
   float* s_win = reinterpret_cast<float*>(smem + kOffWin);
@@ -173,7 +220,9 @@ __global__ void __launch_bounds__(256, 1) k1_dft16(K1Params p, const uint4* __re
   uint64_t* bar_a_free = bars + 1;    // commit: the MMAs that read them are done
   uint64_t* bar_acc_full = bars + 2;  // [2] commit: accumulator b holds a tile
   uint64_t* bar_acc_free = bars + 4;  // [2] 128 arrivals: the epilogue has read accumulator b
+  uint64_t* bar_smp = bars + 6;       // bulk copy of a tile's samples has landed
   unsigned* tmem_slot = reinterpret_cast<unsigned*>(smem + kOffSlot);
+  short* smp = reinterpret_cast<short*>(smem + kOffSamp);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   // the DFT matrix (hi, then lo), already in operand layout: 128 KB, once per CTA
@@ -191,6 +240,7 @@ __global__ void __launch_bounds__(256, 1) k1_dft16(K1Params p, const uint4* __re
     mbar_init(bar_acc_full + 1, 1);
     mbar_init(bar_acc_free + 0, 128);
     mbar_init(bar_acc_free + 1, 128);
+    mbar_init(bar_smp, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -209,62 +259,65 @@ __global__ void __launch_bounds__(256, 1) k1_dft16(K1Params p, const uint4* __re
     unsigned char* a_hi = smem + kOffAhi;
     unsigned char* a_lo = smem + kOffAlo;
     const unsigned idesc = (1u << 4) | ((unsigned)(kN >> 3) << 17) | ((unsigned)(kRows >> 4) << 24);  // f16 x f16 -> f32, K-major both
-    int it = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const TileInfo ti = tile_info(p, tile, tiles_per_stream);
-      if (!ti.live) continue;
+    TileInfo cur = next_tile<true>(p, blockIdx.x, n_tiles, tiles_per_stream, lane);
+    if (ptid == 0 && cur.tile < n_tiles && cur.bulk) bulk_load(smp, cur.bulk, kTileSamples * 2, bar_smp);
+    int it = 0, n_bulk = 0;
+    while (cur.tile < n_tiles) {
+      const TileInfo nxt = next_tile<true>(p, cur.tile + gridDim.x, n_tiles, tiles_per_stream, lane);
       if (it > 0 && !mbar_wait(bar_a_free, (unsigned)(it - 1) & 1u)) break;
-      const Range rg = write_range(p.st.total, p.counts, p.frames, p.done, ti.s);
-      Source src;
-      src.channels = p.g.channels;
-      src.hist = p.hist + (size_t)ti.s * p.hist_stride;
-      src.in = p.in ? p.in + (size_t)ti.s * p.in_stride_frames * p.g.channels : nullptr;
-      src.hist_base = p.st.hist_base[ti.s];
-      src.t_old = rg.t_old;
-      src.t_new = rg.t_new;
-      // unit = (chunk of eight t, window): consecutive threads take consecutive windows
+      // ---- the tile's samples: smp[i] = frame (kt - 1) S + i ---------------------
+      if (cur.bulk) {
+        if (!mbar_wait(bar_smp, (unsigned)n_bulk & 1u)) break;
+        n_bulk++;
+      } else {
+        const Range rg = write_range(p.st.total, p.counts, p.frames, p.done, cur.s);
+        Source src;
+        src.channels = p.g.channels;
+        src.hist = p.hist + (size_t)cur.s * p.hist_stride;
+        src.in = p.in ? p.in + (size_t)cur.s * p.in_stride_frames * p.g.channels : nullptr;
+        src.hist_base = p.st.hist_base[cur.s];
+        src.t_old = rg.t_old;
+        src.t_new = rg.t_new;
+        stage_mono<128, short>(src, (long long)(cur.kt - 1) * kS, kTileSamples, rg.t_new, smp, nullptr, ptid);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      // ---- rows: unit = (chunk of eight t, window); consecutive threads take consecutive windows
+#pragma unroll 1
       for (int u = ptid; u < 15 * 64; u += 128) {
         const int c = u >> 6, w = u & 63;
         const int g = w >> 4, wl = w & 15;
-        const int k = ti.kt + kGroupNew * g + wl - 1;  // wl = 0: the group's halo window
-        const int row = 2 * w;
+        const int wq = kGroupNew * g + wl;  // window kt - 1 + wq (wl = 0: the group's halo window)
+        const int k = cur.kt - 1 + wq;
         uint4 s_hi = make_uint4(0u, 0u, 0u, 0u), s_lo = s_hi, d_hi = s_hi, d_lo = s_hi;
-        if (k >= 0 && k < ti.kB) {
-          const long long f0 = (long long)k * kS;  // first frame of the window
+        if (k >= 0 && k < cur.kB) {
+          const short* x = smp + wq * kS;
           const int nu = 120 + 8 * c, nl = 112 - 8 * c;  // first sample of the upper / lower eight
-          float xu[9], xl[9];                            // [0] = the sample before
-          const int16_t* row_in = src.in ? src.in + (f0 - src.t_old) : nullptr;
-          const bool fast = src.channels == 1 && row_in != nullptr && f0 >= src.t_old && f0 + kW <= src.t_new &&
-                            (reinterpret_cast<size_t>(row_in) & 15) == 0;
-          if (fast) {
-            const uint4 qu = __ldg(reinterpret_cast<const uint4*>(row_in + nu));
-            const uint4 ql = __ldg(reinterpret_cast<const uint4*>(row_in + nl));
-            const unsigned wu[4] = {qu.x, qu.y, qu.z, qu.w}, wlw[4] = {ql.x, ql.y, ql.z, ql.w};
+          const uint4 qu = *reinterpret_cast<const uint4*>(x + nu);
+          const uint4 ql = *reinterpret_cast<const uint4*>(x + nl);
+          const float4 hu0 = *reinterpret_cast<const float4*>(s_win + nu), hu1 = *reinterpret_cast<const float4*>(s_win + nu + 4);
+          const float4 hl0 = *reinterpret_cast<const float4*>(s_win + nl), hl1 = *reinterpret_cast<const float4*>(s_win + nl + 4);
+          float xu[9], xl[9];  // [0] = the sample before
+          xu[0] = (float)x[nu - 1];
+          // the state entering sample 0 is the last sample of the previous window, i.e. sample
+          // P - 1 of this one (speedy.c:416-425); 0 before the first window
+          xl[0] = nl > 0 ? (float)x[nl - 1] : (k >= 1 ? (float)x[kP - 1] : 0.0f);
+          const unsigned wu[4] = {qu.x, qu.y, qu.z, qu.w}, wlw[4] = {ql.x, ql.y, ql.z, ql.w};
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-              xu[1 + 2 * i] = (float)(short)(wu[i] & 0xffffu);
-              xu[2 + 2 * i] = (float)(short)(wu[i] >> 16);
-              xl[1 + 2 * i] = (float)(short)(wlw[i] & 0xffffu);
-              xl[2 + 2 * i] = (float)(short)(wlw[i] >> 16);
-            }
-            xu[0] = (float)__ldg(row_in + nu - 1);
-            // the state entering sample 0 is the last sample of the previous window, i.e. sample
-            // P - 1 of this one (speedy.c:416-425); 0 before the first window
-            xl[0] = nl > 0 ? (float)__ldg(row_in + nl - 1) : (k >= 1 ? (float)__ldg(row_in + kP - 1) : 0.0f);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 9; i++) {
-              xu[i] = (float)src.mono(f0 + nu - 1 + i);
-              xl[i] = (nl - 1 + i >= 0) ? (float)src.mono(f0 + nl - 1 + i) : (k >= 1 ? (float)src.mono(f0 + kP - 1) : 0.0f);
-            }
+          for (int i = 0; i < 4; i++) {
+            xu[1 + 2 * i] = (float)(short)(wu[i] & 0xffffu);
+            xu[2 + 2 * i] = (float)(short)(wu[i] >> 16);
+            xl[1 + 2 * i] = (float)(short)(wlw[i] & 0xffffu);
+            xl[2 + 2 * i] = (float)(short)(wlw[i] >> 16);
           }
+          const float hu[8] = {hu0.x, hu0.y, hu0.z, hu0.w, hu1.x, hu1.y, hu1.z, hu1.w};
+          const float hl[8] = {hl0.x, hl0.y, hl0.z, hl0.w, hl1.x, hl1.y, hl1.z, hl1.w};
           float vu[8], vl[8];
 #pragma unroll
           for (int i = 0; i < 8; i++) {
             // y = x - 0.97 * previous (speedy.c:422, evaluated there in double): 0.97 as a float and
             // its remainder, so the constant carries no error
-            vu[i] = __fmul_rn(__fmaf_rn(-kPreLo, xu[i], __fmaf_rn(-kPreHi, xu[i], xu[i + 1])), s_win[nu + i]);
-            vl[i] = __fmul_rn(__fmaf_rn(-kPreLo, xl[i], __fmaf_rn(-kPreHi, xl[i], xl[i + 1])), s_win[nl + i]);
+            vu[i] = __fmul_rn(__fmaf_rn(-kPreLo, xu[i], __fmaf_rn(-kPreHi, xu[i], xu[i + 1])), hu[i]);
+            vl[i] = __fmul_rn(__fmaf_rn(-kPreLo, xl[i], __fmaf_rn(-kPreHi, xl[i], xl[i + 1])), hl[i]);
           }
           // t = 8c + i pairs sample 120 + t (vu[i]) with sample 119 - t (vl[7 - i])
           float sv[8], dv[8];
@@ -282,7 +335,7 @@ __global__ void __launch_bounds__(256, 1) k1_dft16(K1Params p, const uint4* __re
           split2(dv[4], dv[5], d_hi.z, d_lo.z);
           split2(dv[6], dv[7], d_hi.w, d_lo.w);
         }
-        const int o = op_off(row, 8 * c, kRows);  // (row + 1 is the next 16 bytes)
+        const int o = op_off(2 * w, 8 * c, kRows);  // (row 2w + 1 is the next 16 bytes)
         *reinterpret_cast<uint4*>(a_hi + o) = s_hi;
         *reinterpret_cast<uint4*>(a_hi + o + 16) = d_hi;
         *reinterpret_cast<uint4*>(a_lo + o) = s_lo;
@@ -293,6 +346,8 @@ __global__ void __launch_bounds__(256, 1) k1_dft16(K1Params p, const uint4* __re
       mbar_arrive(bar_a_ready);
       if (ptid == 0) {
         bool ok = mbar_wait(bar_a_ready, (unsigned)it & 1u);
+        // every row thread is done with the samples: the next tile's can start to arrive
+        if (ok && nxt.tile < n_tiles && nxt.bulk) bulk_load(smp, nxt.bulk, kTileSamples * 2, bar_smp);
         const int b = it & 1;
         if (ok && it >= 2) ok = mbar_wait(bar_acc_free + b, (unsigned)((it >> 1) - 1) & 1u);
         if (ok) {
@@ -314,17 +369,19 @@ __global__ void __launch_bounds__(256, 1) k1_dft16(K1Params p, const uint4* __re
         umma_commit(bar_a_free);
         umma_commit(bar_acc_full + b);
       }
+      cur = nxt;
       it++;
     }
+    // no bulk copy may still be in flight when the CTA retires
+    if (ptid == 0 && cur.tile < n_tiles && cur.bulk) mbar_wait(bar_smp, (unsigned)n_bulk & 1u);
   } else {
     // =============================== epilogue =====================================
-    // thread = accumulator row: lane pair (2 wl, 2 wl + 1) = (s-row, d'-row) of window wl of group `warp`
+    // thread = accumulator row: lane pair (2 wl, 2 wl + 1) = (s-row, d'-row) of window wl of group `warp`;
+    // this lane's bins: role 0: k = i (i = 0 .. 120), role 1: k = 240 - i (i = 0 .. 119)
     const int role = lane & 1, wl = lane >> 1;
-    const int last_i = role ? 119 : 120;  // this lane's bins: role 0: k = i (1 .. 120), role 1: k = 240 - i (121 .. 239)
     int it = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const TileInfo ti = tile_info(p, tile, tiles_per_stream);
-      if (!ti.live) continue;
+    for (TileInfo ti = next_tile<false>(p, blockIdx.x, n_tiles, tiles_per_stream, lane); ti.tile < n_tiles;
+         ti = next_tile<false>(p, ti.tile + gridDim.x, n_tiles, tiles_per_stream, lane), it++) {
       const int b = it & 1;
       if (!mbar_wait(bar_acc_full + b, (unsigned)(it >> 1) & 1u)) break;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -332,8 +389,8 @@ __global__ void __launch_bounds__(256, 1) k1_dft16(K1Params p, const uint4* __re
       const int k = ti.kt + kGroupNew * warp + wl - 1;
       const bool out = wl >= 1 && k < ti.kB;
       float* tap = nullptr;
-      if (p.tap_spec && out) tap = p.tap_spec + ((size_t)ti.s * p.tap_stride + (k - ti.kA)) * 480;
-      // pass 1: power and log2 power of this lane's bins; energy and peak
+      if (TAP && out) tap = p.tap_spec + ((size_t)ti.s * p.tap_stride + (k - ti.kA)) * 480;
+      // pass 1: power and log2 power of this lane's bins; energy and peak (bins 0 and N/2 stay out of both)
       float l[128];
       float e = 0.0f, mx = 0.0f;
 #pragma unroll
@@ -344,19 +401,23 @@ __global__ void __launch_bounds__(256, 1) k1_dft16(K1Params p, const uint4* __re
 #pragma unroll
         for (int j = 0; j < 32; j++) {
           const int i = 32 * c + j;
+          if (i > 120) continue;
           // the partner's column 240 - i (= 113 + (127 - i)): Re and Im of the same bin meet here
           const float other = __shfl_xor_sync(0xffffffffu, hi[31 - j], 1);
           const float q = __fadd_rn(__fmul_rn(lo[j], lo[j]), __fmul_rn(other, other));  // 2^26 |X|^2
           l[i] = __log2f(q);
-          const bool counted = i >= 1 && i <= last_i;  // bins 0 and N/2 are not part of the energy
-          const float qc = counted ? q : 0.0f;
-          e += qc;
-          mx = fmaxf(mx, qc);
-          if (tap && i <= last_i) {
-            const float m = __fsqrt_rn(q) * 1.220703125e-4f;  // 2^-13
-            const int kbin = role ? 240 - i : i;
-            tap[kbin] = m;
-            if (kbin != 0 && kbin != 240) tap[480 - kbin] = m;
+          if (i >= 1) {
+            const float qc = (i < 120 || role == 0) ? q : 0.0f;
+            e += qc;
+            mx = fmaxf(mx, qc);
+          }
+          if (TAP) {
+            if (tap && (i < 120 || role == 0)) {
+              const float m = __fsqrt_rn(q) * 1.220703125e-4f;  // 2^-13
+              const int kbin = role ? 240 - i : i;
+              tap[kbin] = m;
+              if (kbin != 0 && kbin != 240) tap[480 - kbin] = m;
+            }
           }
         }
       }
@@ -376,11 +437,11 @@ __global__ void __launch_bounds__(256, 1) k1_dft16(K1Params p, const uint4* __re
 #pragma unroll
       for (int i = 1; i <= 120; i++) {
         const float ll = __shfl_up_sync(0xffffffffu, l[i], 2);  // the same bin of the previous window
-        if (i <= last_i && l[i] > thr && ll > thr) acc += fabsf((l[i] - ll) + d2);
+        const float term = fabsf((l[i] - ll) + d2);
+        if ((i < 120 || role == 0) && l[i] > thr && ll > thr) acc += term;
       }
       acc += __shfl_xor_sync(0xffffffffu, acc, 1);
       if (out && role == 0) p.feat[(size_t)ti.s * p.feat_stride + (k - ti.kA)] = make_float2(e, acc * 0.34657359027997264f);  // ln2 / 2
-      it++;
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -428,8 +489,8 @@ cudaError_t launch_k1_dft16(const K1Params& p, cudaStream_t stream) {
   cudaError_t e = cudaSuccess;
   const uint4* dft = dft_matrix(&e);
   if (!dft) return e;
-  static SmemOptIn opt;
-  if ((e = opt.ensure(k1_dft16, kSmemBytes)) != cudaSuccess) return e;
+  static SmemOptIn opt, opt_tap;
+  if ((e = (p.tap_spec ? opt_tap.ensure(k1_dft16<true>, kSmemBytes) : opt.ensure(k1_dft16<false>, kSmemBytes))) != cudaSuccess) return e;
   static int sms[kMaxDevices];
   int dev = 0;
   cudaGetDevice(&dev);
@@ -438,7 +499,8 @@ cudaError_t launch_k1_dft16(const K1Params& p, cudaStream_t stream) {
   const int tiles_per_stream = (p.max_new_frames + kTileNew - 1) / kTileNew;
   const long long n_tiles = (long long)tiles_per_stream * p.n_streams;
   const int grid = (int)(n_tiles < n_sm ? n_tiles : n_sm);
-  k1_dft16<<<grid, 256, kSmemBytes, stream>>>(p, dft, (int)n_tiles, tiles_per_stream);
+  if (p.tap_spec) k1_dft16<true><<<grid, 256, kSmemBytes, stream>>>(p, dft, (int)n_tiles, tiles_per_stream);
+  else k1_dft16<false><<<grid, 256, kSmemBytes, stream>>>(p, dft, (int)n_tiles, tiles_per_stream);
   count_launch();
   return cudaGetLastError();
 }
