@@ -23,17 +23,18 @@
 // same 1e-4 bars).  The accumulator holds 2^13 X; everything downstream works on log2 |X|^2
 // differences and on the energy, rescaled exactly (powers of two).
 //
-// Shape.  One persistent CTA per SM, 8 warps.  A tile is 64 windows = 128 rows: four groups of
+// Shape.  One persistent CTA per SM, 16 warps.  A tile is 64 windows = 128 rows: four groups of
 // one halo window (the previous window, recomputed: its spectrum is the other operand of the
 // spectral difference) + 15 new ones, rows interleaved (2w: s, 2w + 1: d').
-//   warps 4-7  prepare the rows: the tile's samples arrive in shared memory as one TMA bulk copy
+//   warps 8-15 prepare the rows: the tile's samples arrive in shared memory as one TMA bulk copy
 //              (cp.async.bulk + mbarrier, issued a tile ahead; tiles that touch the carried history
 //              are staged by the warps themselves), then pre-emphasis, window, fold and split into
 //              the A operand (no-swizzle canonical layout: core matrices of 8 rows x 16 bytes);
 //              one elected thread issues the 24 tcgen05.mma of the tile and commits to mbarriers;
-//   warps 0-3  read the accumulator (tcgen05.ld, thread = row): lane pairs (s-row, d'-row) trade
-//              the mirrored halves by shuffle, each lane takes half of the bins: power, log2,
-//              energy, 40 dB gate, spectral difference against the window two lanes down.
+//   warps 0-7  read the accumulator (tcgen05.ld, thread = row, two warps per 32 rows with half of
+//              the columns each): lane pairs (s-row, d'-row) trade the mirrored columns by shuffle,
+//              each lane takes the bins of one side: power, log2, energy, 40 dB gate, spectral
+//              difference against the window two lanes down.
 // The accumulator is double-buffered in tensor memory (2 x 256 columns), so the epilogue of tile i
 // runs under the preparation and the MMAs of tile i + 1.  Every wait is bounded (a wrong barrier
 // must not hang the device): on a time-out the kernel sets an error word and drains.
@@ -65,7 +66,8 @@ constexpr int kOffBars = kOffWin + 1024;   // 7 mbarriers
 constexpr int kOffSlot = kOffBars + 64;    // tensor-memory base address
 constexpr int kOffSamp = kOffSlot + 64;    // short[kTileSamples]: the tile's samples (windows kt-1 .. kt+59)
 constexpr int kTileSamples = kTileNew * kS + kW;  // 9840 samples = 19680 bytes
-constexpr int kSmemBytes = kOffSamp + kTileSamples * 2 + 32;
+constexpr int kOffXch = kOffSamp + kTileSamples * 2 + 32;  // float2[2][4][16]: the two column halves of a window meet here
+constexpr int kSmemBytes = kOffXch + 2 * 4 * 16 * 8;
 
 // element (r, k) of an [R x 128] K-major fp16 operand in the no-swizzle canonical layout: core
 // matrices of 8 rows x 16 bytes contiguous along the rows (stride byte offset 128), the 8-element
@@ -136,22 +138,19 @@ __device__ __forceinline__ void umma_f16(unsigned tmem_d, uint64_t da, uint64_t 
       "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// 32 consecutive columns of this thread's tensor-memory lane
-__device__ __forceinline__ void tmem_ld32(unsigned taddr, float (&v)[32]) {
-  unsigned r[32];
+// 16 consecutive columns of this thread's tensor-memory lane
+__device__ __forceinline__ void tmem_ld16(unsigned taddr, float (&v)[16]) {
+  unsigned r[16];
   asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-  for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
+  for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
 }
 
 // x = hi + lo with hi on an fp16 grid (top 11 bits, by truncation: exact) and lo the exact
@@ -212,14 +211,14 @@ __device__ __forceinline__ TileInfo next_tile(const K1Params& p, int tile, int n
 }  // namespace
 
 template <bool TAP>
-__global__ void __launch_bounds__(256, 1) k1_dft16(K1Params p, const uint4* __restrict__ dft_hi_lo, int n_tiles, int tiles_per_stream) {
+__global__ void __launch_bounds__(512, 1) k1_dft16(K1Params p, const uint4* __restrict__ dft_hi_lo, int n_tiles, int tiles_per_stream) {
   extern __shared__ __align__(1024) unsigned char smem[];
   float* s_win = reinterpret_cast<float*>(smem + kOffWin);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
-  uint64_t* bar_a_ready = bars + 0;   // 128 arrivals: the rows of a tile are in shared memory
+  uint64_t* bar_a_ready = bars + 0;   // 256 arrivals: the rows of a tile are in shared memory
   uint64_t* bar_a_free = bars + 1;    // commit: the MMAs that read them are done
   uint64_t* bar_acc_full = bars + 2;  // [2] commit: accumulator b holds a tile
-  uint64_t* bar_acc_free = bars + 4;  // [2] 128 arrivals: the epilogue has read accumulator b
+  uint64_t* bar_acc_free = bars + 4;  // [2] 256 arrivals: the epilogue has read accumulator b
   uint64_t* bar_smp = bars + 6;       // bulk copy of a tile's samples has landed
   unsigned* tmem_slot = reinterpret_cast<unsigned*>(smem + kOffSlot);
   short* smp = reinterpret_cast<short*>(smem + kOffSamp);
@@ -228,18 +227,18 @@ __global__ void __launch_bounds__(256, 1) k1_dft16(K1Params p, const uint4* __re
   // the DFT matrix (hi, then lo), already in operand layout: 128 KB, once per CTA
   {
     uint4* dst = reinterpret_cast<uint4*>(smem + kOffBhi);
-    for (int i = tid; i < 131072 / 16; i += 256) dst[i] = dft_hi_lo[i];
+    for (int i = tid; i < 131072 / 16; i += 512) dst[i] = dft_hi_lo[i];
     uint4* a = reinterpret_cast<uint4*>(smem + kOffAhi);  // rows start as zeros (the K padding stays zero)
-    for (int i = tid; i < 65536 / 16; i += 256) a[i] = make_uint4(0u, 0u, 0u, 0u);
-    for (int i = tid; i < kW; i += 256) s_win[i] = p.window[i] * 0.25f;  // Hamming / 4: rows at the int16 scale / 4
+    for (int i = tid; i < 65536 / 16; i += 512) a[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < kW; i += 512) s_win[i] = p.window[i] * 0.25f;  // Hamming / 4: rows at the int16 scale / 4
   }
   if (tid == 0) {
-    mbar_init(bar_a_ready, 128);
+    mbar_init(bar_a_ready, 256);
     mbar_init(bar_a_free, 1);
     mbar_init(bar_acc_full + 0, 1);
     mbar_init(bar_acc_full + 1, 1);
-    mbar_init(bar_acc_free + 0, 128);
-    mbar_init(bar_acc_free + 1, 128);
+    mbar_init(bar_acc_free + 0, 256);
+    mbar_init(bar_acc_free + 1, 256);
     mbar_init(bar_smp, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -253,9 +252,9 @@ __global__ void __launch_bounds__(256, 1) k1_dft16(K1Params p, const uint4* __re
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const unsigned tmem = *tmem_slot;
 
-  if (warp >= 4) {
+  if (warp >= 8) {
     // =========================== rows + MMA issue ===============================
-    const int ptid = tid - 128;
+    const int ptid = tid - 256;
     unsigned char* a_hi = smem + kOffAhi;
     unsigned char* a_lo = smem + kOffAlo;
     const unsigned idesc = (1u << 4) | ((unsigned)(kN >> 3) << 17) | ((unsigned)(kRows >> 4) << 24);  // f16 x f16 -> f32, K-major both
@@ -278,12 +277,12 @@ __global__ void __launch_bounds__(256, 1) k1_dft16(K1Params p, const uint4* __re
         src.hist_base = p.st.hist_base[cur.s];
         src.t_old = rg.t_old;
         src.t_new = rg.t_new;
-        stage_mono<128, short>(src, (long long)(cur.kt - 1) * kS, kTileSamples, rg.t_new, smp, nullptr, ptid);
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        stage_mono<256, short>(src, (long long)(cur.kt - 1) * kS, kTileSamples, rg.t_new, smp, nullptr, ptid);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
       // ---- rows: unit = (chunk of eight t, window); consecutive threads take consecutive windows
 #pragma unroll 1
-      for (int u = ptid; u < 15 * 64; u += 128) {
+      for (int u = ptid; u < 15 * 64; u += 256) {
         const int c = u >> 6, w = u & 63;
         const int g = w >> 4, wl = w & 15;
         const int wq = kGroupNew * g + wl;  // window kt - 1 + wq (wl = 0: the group's halo window)
@@ -376,43 +375,47 @@ __global__ void __launch_bounds__(256, 1) k1_dft16(K1Params p, const uint4* __re
     if (ptid == 0 && cur.tile < n_tiles && cur.bulk) mbar_wait(bar_smp, (unsigned)n_bulk & 1u);
   } else {
     // =============================== epilogue =====================================
-    // thread = accumulator row: lane pair (2 wl, 2 wl + 1) = (s-row, d'-row) of window wl of group `warp`;
-    // this lane's bins: role 0: k = i (i = 0 .. 120), role 1: k = 240 - i (i = 0 .. 119)
+    // thread = accumulator row: lane pair (2 wl, 2 wl + 1) = (s-row, d'-row) of window wl of group `grp`;
+    // a lane's bins: role 0: k = i, role 1: k = 240 - i, and the i range 0 .. 120 is cut in two halves
+    // (0 .. 60, 61 .. 120) taken by warps grp and grp + 4, which read the same tensor-memory lanes
+    const int grp = warp & 3, half = warp >> 2;
     const int role = lane & 1, wl = lane >> 1;
+    const int i0 = 61 * half;
+    float2* xch = reinterpret_cast<float2*>(smem + kOffXch);  // [2 halves][4 groups][16 windows]: (energy, peak), then lsd
     int it = 0;
     for (TileInfo ti = next_tile<false>(p, blockIdx.x, n_tiles, tiles_per_stream, lane); ti.tile < n_tiles;
          ti = next_tile<false>(p, ti.tile + gridDim.x, n_tiles, tiles_per_stream, lane), it++) {
       const int b = it & 1;
       if (!mbar_wait(bar_acc_full + b, (unsigned)(it >> 1) & 1u)) break;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const unsigned row_base = tmem + ((unsigned)(warp * 32) << 16) + (unsigned)(b * kN);
-      const int k = ti.kt + kGroupNew * warp + wl - 1;
+      const unsigned row_base = tmem + ((unsigned)(grp * 32) << 16) + (unsigned)(b * kN);
+      const int k = ti.kt + kGroupNew * grp + wl - 1;
       const bool out = wl >= 1 && k < ti.kB;
       float* tap = nullptr;
       if (TAP && out) tap = p.tap_spec + ((size_t)ti.s * p.tap_stride + (k - ti.kA)) * 480;
       // pass 1: power and log2 power of this lane's bins; energy and peak (bins 0 and N/2 stay out of both)
-      float l[128];
+      float l[64];
       float e = 0.0f, mx = 0.0f;
 #pragma unroll
       for (int c = 0; c < 4; c++) {
-        float lo[32], hi[32];
-        tmem_ld32(row_base + 32u * c, lo);                // own columns i = 32c .. 32c + 31
-        tmem_ld32(row_base + 113u + 32u * (3 - c), hi);   // own columns 113 + m, m = 96 - 32c .. 127 - 32c
+        float lo[16], hi[16];
+        tmem_ld16(row_base + (unsigned)(i0 + 16 * c), lo);         // own columns i = i0 + 16c + j
+        tmem_ld16(row_base + (unsigned)(225 - i0 - 16 * c), hi);   // own columns 240 - i for those i, backwards
 #pragma unroll
-        for (int j = 0; j < 32; j++) {
-          const int i = 32 * c + j;
-          if (i > 120) continue;
-          // the partner's column 240 - i (= 113 + (127 - i)): Re and Im of the same bin meet here
-          const float other = __shfl_xor_sync(0xffffffffu, hi[31 - j], 1);
-          const float q = __fadd_rn(__fmul_rn(lo[j], lo[j]), __fmul_rn(other, other));  // 2^26 |X|^2
-          l[i] = __log2f(q);
-          if (i >= 1) {
-            const float qc = (i < 120 || role == 0) ? q : 0.0f;
-            e += qc;
-            mx = fmaxf(mx, qc);
-          }
+        for (int j = 0; j < 16; j++) {
+          const int ii = 16 * c + j;  // i - i0
+          if (ii > 60) continue;
+          const int i = i0 + ii;
+          // the partner's column 240 - i: Re and Im of the same bin meet here
+          const float other = __shfl_xor_sync(0xffffffffu, hi[15 - j], 1);
+          const float q = __fmaf_rn(lo[j], lo[j], __fmul_rn(other, other));  // 2^26 |X|^2
+          l[ii] = __log2f(q);
+          const bool counted = i >= 1 && i <= 120 && (i < 120 || role == 0);  // (i = 121 only pads the upper half)
+          const float qc = counted ? q : 0.0f;
+          e += qc;
+          mx = fmaxf(mx, qc);
           if (TAP) {
-            if (tap && (i < 120 || role == 0)) {
+            if (tap && i <= 120 && (i < 120 || role == 0)) {
               const float m = __fsqrt_rn(q) * 1.220703125e-4f;  // 2^-13
               const int kbin = role ? 240 - i : i;
               tap[kbin] = m;
@@ -424,8 +427,16 @@ __global__ void __launch_bounds__(256, 1) k1_dft16(K1Params p, const uint4* __re
       // the accumulator is in registers now: hand it back to the MMA issuer
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(bar_acc_free + b);
-      e = (e + __shfl_xor_sync(0xffffffffu, e, 1)) * 1.4901161193847656e-08f;  // 2^-26: the /32768 scale of speedy.c:558
+      // energy and peak of the window: the two roles by shuffle, the two halves through shared memory
+      e += __shfl_xor_sync(0xffffffffu, e, 1);
       mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      if (role == 0) xch[(half * 4 + grp) * 16 + wl] = make_float2(e, mx);
+      asm volatile("bar.sync %0, 64;" ::"r"(2 + grp) : "memory");
+      {
+        const float2 o = xch[((half ^ 1) * 4 + grp) * 16 + wl];
+        e = (e + o.x) * 1.4901161193847656e-08f;  // 2^-26: the /32768 scale of speedy.c:558
+        mx = fmaxf(mx, o.y);
+      }
       // pass 2, speedy.c:705-719 in the log2 domain: with n_i = |X_i| / (sqrt(E) + eps),
       //   log(n_c / n_l) = ln2 * (0.5 (lp_c - lp_l) + (linv_c - linv_l)),  lp = log2 |X|^2, linv = -log2(sqrt(E) + eps);
       //   |X_i| > max|X| / 100  <=>  lp_i > log2(max p) - log2(1e4)
@@ -435,13 +446,21 @@ __global__ void __launch_bounds__(256, 1) k1_dft16(K1Params p, const uint4* __re
       const float d2 = 2.0f * (linv - linv_last);
       float acc = 0.0f;
 #pragma unroll
-      for (int i = 1; i <= 120; i++) {
-        const float ll = __shfl_up_sync(0xffffffffu, l[i], 2);  // the same bin of the previous window
-        const float term = fabsf((l[i] - ll) + d2);
-        if ((i < 120 || role == 0) && l[i] > thr && ll > thr) acc += term;
+      for (int ii = 0; ii <= 60; ii++) {
+        const int i = i0 + ii;
+        const float ll = __shfl_up_sync(0xffffffffu, l[ii], 2);  // the same bin of the previous window
+        const float term = fabsf((l[ii] - ll) + d2);
+        if (i >= 1 && i <= 120 && (i < 120 || role == 0) && l[ii] > thr && ll > thr) acc += term;
       }
       acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-      if (out && role == 0) p.feat[(size_t)ti.s * p.feat_stride + (k - ti.kA)] = make_float2(e, acc * 0.34657359027997264f);  // ln2 / 2
+      asm volatile("bar.sync %0, 64;" ::"r"(2 + grp) : "memory");  // (both halves have read the energies)
+      if (half == 1 && role == 0) xch[(4 + grp) * 16 + wl].x = acc;
+      asm volatile("bar.sync %0, 64;" ::"r"(2 + grp) : "memory");
+      if (half == 0 && out && role == 0) {
+        acc += xch[(4 + grp) * 16 + wl].x;
+        p.feat[(size_t)ti.s * p.feat_stride + (k - ti.kA)] = make_float2(e, acc * 0.34657359027997264f);  // ln2 / 2
+      }
+      asm volatile("bar.sync %0, 64;" ::"r"(2 + grp) : "memory");  // (the exchange slots are free for the next tile)
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -499,8 +518,8 @@ cudaError_t launch_k1_dft16(const K1Params& p, cudaStream_t stream) {
   const int tiles_per_stream = (p.max_new_frames + kTileNew - 1) / kTileNew;
   const long long n_tiles = (long long)tiles_per_stream * p.n_streams;
   const int grid = (int)(n_tiles < n_sm ? n_tiles : n_sm);
-  if (p.tap_spec) k1_dft16<true><<<grid, 256, kSmemBytes, stream>>>(p, dft, (int)n_tiles, tiles_per_stream);
-  else k1_dft16<false><<<grid, 256, kSmemBytes, stream>>>(p, dft, (int)n_tiles, tiles_per_stream);
+  if (p.tap_spec) k1_dft16<true><<<grid, 512, kSmemBytes, stream>>>(p, dft, (int)n_tiles, tiles_per_stream);
+  else k1_dft16<false><<<grid, 512, kSmemBytes, stream>>>(p, dft, (int)n_tiles, tiles_per_stream);
   count_launch();
   return cudaGetLastError();
 }

@@ -980,7 +980,7 @@ cudaError_t launch_k1(const K1Params& p, cudaStream_t stream) {
   // 16 kHz mono writes of a second or more: the tensor-core shape (k1_dft16.cu), SPEEDY_K1_TC=0 turns it off
   {
     const char* e = getenv("SPEEDY_K1_TC");
-    const int on = e ? atoi(e) : 0;
+    const int on = e ? atoi(e) : 1;
     if (on && p.frames - p.done >= (long long)p.g.rate && k1_dft16_supported(p)) return launch_k1_dft16(p, stream);
   }
   K1Params q = p;
