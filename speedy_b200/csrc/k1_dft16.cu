@@ -23,9 +23,10 @@
 // same 1e-4 bars).  The accumulator holds 2^13 X; everything downstream works on log2 |X|^2
 // differences and on the energy, rescaled exactly (powers of two).
 //
-// Shape.  One persistent CTA per SM, 16 warps.  A tile is 64 windows = 128 rows: four groups of
-// one halo window (the previous window, recomputed: its spectrum is the other operand of the
-// spectral difference) + 15 new ones, rows interleaved (2w: s, 2w + 1: d').
+// Shape.  One persistent CTA per SM, 16 warps.  A tile is 64 window slots = 128 rows (2w: s,
+// 2w + 1: d'), four groups of 16; a group holds runs of consecutive windows of a stream, each a halo
+// window (the previous window, recomputed: its spectrum is the other operand of the spectral
+// difference) + up to 15 new ones: one long run, or several short ones of different streams (make_tiling).
 //   warps 8-15 prepare the rows: the tile's samples arrive in shared memory as one TMA bulk copy
 //              (cp.async.bulk + mbarrier, issued a tile ahead; tiles that touch the carried history
 //              are staged by the warps themselves), then pre-emphasis, window, fold and split into
@@ -64,10 +65,12 @@ constexpr int kOffBhi = 0, kOffBlo = 65536, kOffAhi = 131072, kOffAlo = 163840;
 constexpr int kOffWin = 196608;            // float[240]: Hamming / 4
 constexpr int kOffBars = kOffWin + 1024;   // 7 mbarriers
 constexpr int kOffSlot = kOffBars + 64;    // tensor-memory base address
-constexpr int kOffSamp = kOffSlot + 64;    // short[kTileSamples]: the tile's samples (windows kt-1 .. kt+59)
-constexpr int kTileSamples = kTileNew * kS + kW;  // 9840 samples = 19680 bytes
-constexpr int kOffXch = kOffSamp + kTileSamples * 2 + 32;  // float2[2][4][16]: the two column halves of a window meet here
-constexpr int kSmemBytes = kOffXch + 2 * 4 * 16 * 8;
+constexpr int kOffSamp = kOffSlot + 64;    // short[kSampCap]: the samples of the tile's runs
+constexpr int kSampCap = 12800;            // 32 runs of 400 (one new window + halo each) is the largest tile
+constexpr int kOffXch = kOffSamp + kSampCap * 2;       // float2[2][4][16]: the two column halves of a window meet here
+constexpr int kOffSlots = kOffXch + 2 * 4 * 16 * 8;    // Slot[3][64]: what each row pair of a tile is
+constexpr int kSmemBytes = kOffSlots + 3 * 64 * 16 + 16;
+constexpr int kSpanSamples = kTileNew * kS + kW;  // one stream's 61 consecutive windows: 9840 samples
 
 // element (r, k) of an [R x 128] K-major fp16 operand in the no-swizzle canonical layout: core
 // matrices of 8 rows x 16 bytes contiguous along the rows (stride byte offset 128), the 8-element
@@ -163,66 +166,102 @@ __device__ __forceinline__ void split2(float a, float b, unsigned& hi, unsigned&
   lo = *reinterpret_cast<const unsigned*>(&l);
 }
 
-struct TileInfo {
-  int tile, s, kt, kB, kA;  // tile id, stream, first new window, windows analysed after this launch, row base
-  const int16_t* bulk;      // rows only: the tile's samples as one aligned span of the caller's buffer, or null
+// How a launch is cut into tiles.  Every stream has at most n = max_new_frames new windows.  A run is
+// a halo window (the predecessor of its first new window, recomputed) followed by up to 15 new ones,
+// consecutive windows of one stream; the 16 window slots of a warp-sized group of rows hold one long
+// run (n > 15: the stream is cut into runs of 15) or as many short ones as fit (n <= 15: one run per
+// stream, 16 / (n + 1) streams per group: a 10 ms streaming write of thousands of sessions packs 32
+// streams into a tile).  A tile is four groups.
+struct Tiling {
+  int new_per_run, slots_per_run, runs_per_group, runs_per_stream, run_samples, total_runs, n_tiles;
+};
+__host__ __device__ inline Tiling make_tiling(int n, int n_streams) {
+  Tiling t;
+  t.new_per_run = n < kGroupNew ? n : kGroupNew;
+  t.slots_per_run = t.new_per_run + 1;
+  t.runs_per_group = 16 / t.slots_per_run;
+  t.runs_per_stream = (n + kGroupNew - 1) / kGroupNew;
+  t.run_samples = t.new_per_run * kS + kW;
+  t.total_runs = t.runs_per_stream * n_streams;
+  const int groups = (t.total_runs + t.runs_per_group - 1) / t.runs_per_group;
+  t.n_tiles = (groups + kGroups - 1) / kGroups;
+  return t;
+}
+
+// One window slot (a row pair) of a tile.
+struct __align__(16) Slot {
+  int s;      // stream
+  int k;      // window (k = -1: the halo before a stream's first window: zeros)
+  int kA;     // the stream's scratch rows count from this window
+  int flags;  // 1: a window of this launch (results go out)  2: rows carry data (0 <= k < windows analysed)
+              // bits 8..15: position in its run, bits 16..: the run's index in the tile
 };
 
-// The next tile of this CTA (id >= `tile`, stride gridDim.x) that has windows to analyse; .tile >= n_tiles: none.
-// Lane 0 works it out (64-bit divisions) and the warp shares it.
-template <bool ROWS>
-__device__ __forceinline__ TileInfo next_tile(const K1Params& p, int tile, int n_tiles, int tiles_per_stream, int lane) {
-  TileInfo t;
-  t.bulk = nullptr;
-  for (;; tile += gridDim.x) {
-    t.tile = tile;
-    if (tile >= n_tiles) return t;
-    t.s = tile / tiles_per_stream;
-    int kt = 0, kB = 0, kA = 0, live = 0;
-    unsigned long long bulk = 0ULL;
-    if (lane == 0) {
-      const int j = tile - t.s * tiles_per_stream;
-      const Range rg = write_range(p.st.total, p.counts, p.frames, p.done, t.s);
-      kA = frames_analyzed(p.g, rg.t_old);
-      const int kD = frames_analyzed(p.g, rg.t_done);
-      kB = frames_analyzed(p.g, rg.t_new);
-      kt = kD + j * kTileNew;
-      live = kt < kB && p.st.nonlinear[t.s] != 0.0f;  // soniclib.c:397-399: Speedy is bypassed in the linear mode
-      if (ROWS && live && p.g.channels == 1 && p.in != nullptr) {
-        // frames [(kt - 1) S, (kt + 59) S + W) straight from the caller's buffer?  (Not the first
-        // tile of a write: its halo window reaches into the carried history.)
-        const long long f0 = (long long)(kt - 1) * kS;
-        if (f0 >= rg.t_old && f0 + kTileSamples <= rg.t_new) {
-          const int16_t* src = p.in + (size_t)t.s * p.in_stride_frames + (f0 - rg.t_old);
-          if ((reinterpret_cast<size_t>(src) & 15) == 0) bulk = reinterpret_cast<unsigned long long>(src);
-        }
-      }
-    }
-    live = __shfl_sync(0xffffffffu, live, 0);
-    if (!live) continue;
-    t.kt = __shfl_sync(0xffffffffu, kt, 0);
-    t.kB = __shfl_sync(0xffffffffu, kB, 0);
-    t.kA = __shfl_sync(0xffffffffu, kA, 0);
-    if (ROWS) t.bulk = reinterpret_cast<const int16_t*>(__shfl_sync(0xffffffffu, bulk, 0));
-    return t;
-  }
+// speedy's frames_analyzed for W = 240, S = 160 (soniclib.c:440-444), in 32 bits when the total allows
+__device__ __forceinline__ int windows_after(long long total) {
+  if (total < kW + 1) return 0;
+  if (total < (1LL << 31)) return ((int)total - kW - 1) / kS + 1;
+  return (int)((total - kW - 1) / kS) + 1;
+}
+
+__device__ __forceinline__ Slot make_slot(const K1Params& p, const Tiling& tl, int tile, int w) {
+  Slot sl;
+  sl.s = 0; sl.k = 0; sl.kA = 0; sl.flags = 0;
+  const int g = w >> 4, wl = w & 15;
+  const int r_local = wl / tl.slots_per_run, pos = wl - r_local * tl.slots_per_run;
+  const int run = (tile * kGroups + g) * tl.runs_per_group + r_local;
+  sl.flags = (pos << 8) | ((g * tl.runs_per_group + r_local) << 16);
+  if (r_local >= tl.runs_per_group || run >= tl.total_runs) return sl;
+  sl.s = run / tl.runs_per_stream;
+  const int j = run - sl.s * tl.runs_per_stream;
+  if (p.st.nonlinear[sl.s] == 0.0f) return sl;  // soniclib.c:397-399: Speedy is bypassed in the linear mode
+  const Range rg = write_range(p.st.total, p.counts, p.frames, p.done, sl.s);
+  sl.kA = windows_after(rg.t_old);
+  const int kD = windows_after(rg.t_done), kB = windows_after(rg.t_new);
+  sl.k = kD + kGroupNew * j + pos - 1;
+  if (kD + kGroupNew * j >= kB) return sl;  // the run has no new window
+  if (sl.k >= 0 && sl.k < kB) sl.flags |= 2;
+  if (pos >= 1 && sl.k < kB) sl.flags |= 1;
+  return sl;
+}
+
+// Long launches: can the tile's samples -- one stream, four consecutive runs, frames
+// [(k0 - 1) S, (k0 + 59) S + W) -- come as one aligned bulk copy straight from the caller's buffer?
+// (Not the first tile of a write: its halo window reaches into the carried history.)
+__device__ __forceinline__ const int16_t* tile_bulk_src(const K1Params& p, const Tiling& tl, int tile) {
+  if (tile >= tl.n_tiles || tl.runs_per_group != 1 || p.g.channels != 1 || p.in == nullptr) return nullptr;
+  const int run0 = tile * kGroups;
+  const int s = run0 / tl.runs_per_stream, j = run0 - s * tl.runs_per_stream;
+  if (j + kGroups > tl.runs_per_stream || p.st.nonlinear[s] == 0.0f) return nullptr;
+  const Range rg = write_range(p.st.total, p.counts, p.frames, p.done, s);
+  const int kD = windows_after(rg.t_done);
+  const long long f0 = (long long)(kD + kGroupNew * j - 1) * kS;
+  if (f0 < rg.t_old || f0 + kSpanSamples > rg.t_new) return nullptr;
+  const int16_t* src = p.in + (size_t)s * p.in_stride_frames + (f0 - rg.t_old);
+  return (reinterpret_cast<size_t>(src) & 15) == 0 ? src : nullptr;
 }
 
 }  // namespace
 
 template <bool TAP>
-__global__ void __launch_bounds__(512, 1) k1_dft16(K1Params p, const uint4* __restrict__ dft_hi_lo, int n_tiles, int tiles_per_stream) {
+__global__ void __launch_bounds__(512, 1) k1_dft16(K1Params p, const uint4* __restrict__ dft_hi_lo, Tiling tl) {
   extern __shared__ __align__(1024) unsigned char smem[];
   float* s_win = reinterpret_cast<float*>(smem + kOffWin);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
   uint64_t* bar_a_ready = bars + 0;   // 256 arrivals: the rows of a tile are in shared memory
   uint64_t* bar_a_free = bars + 1;    // commit: the MMAs that read them are done
   uint64_t* bar_acc_full = bars + 2;  // [2] commit: accumulator b holds a tile
-  uint64_t* bar_acc_free = bars + 4;  // [2] 256 arrivals: the epilogue has read accumulator b
+  uint64_t* bar_acc_free = bars + 4;  // [2] 256 arrivals: the epilogue has read accumulator b (and the tile's slots)
   uint64_t* bar_smp = bars + 6;       // bulk copy of a tile's samples has landed
   unsigned* tmem_slot = reinterpret_cast<unsigned*>(smem + kOffSlot);
+  unsigned long long* bulk_word = reinterpret_cast<unsigned long long*>(smem + kOffSlot + 16);  // this tile's bulk source (or 0)
   short* smp = reinterpret_cast<short*>(smem + kOffSamp);
+  // [3][64]: tile it uses table it % 3.  Three are enough without a barrier of their own: the rows of
+  // tile it are written after the MMAs of tile it - 1 have completed, and those were issued only after
+  // the epilogue of tile it - 3 had handed its accumulator back (it copies its slot first)
+  Slot* slots = reinterpret_cast<Slot*>(smem + kOffSlots);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_tiles = tl.n_tiles;
 
   // the DFT matrix (hi, then lo), already in operand layout: 128 KB, once per CTA
   {
@@ -254,42 +293,59 @@ __global__ void __launch_bounds__(512, 1) k1_dft16(K1Params p, const uint4* __re
 
   if (warp >= 8) {
     // =========================== rows + MMA issue ===============================
-    const int ptid = tid - 256;
+    const int ptid = tid - 256, pwarp = warp - 8;
     unsigned char* a_hi = smem + kOffAhi;
     unsigned char* a_lo = smem + kOffAlo;
     const unsigned idesc = (1u << 4) | ((unsigned)(kN >> 3) << 17) | ((unsigned)(kRows >> 4) << 24);  // f16 x f16 -> f32, K-major both
-    TileInfo cur = next_tile<true>(p, blockIdx.x, n_tiles, tiles_per_stream, lane);
-    if (ptid == 0 && cur.tile < n_tiles && cur.bulk) bulk_load(smp, cur.bulk, kTileSamples * 2, bar_smp);
+    // (thread 0 looks one tile ahead for the bulk copy)
+    const int16_t* bulk_cur = ptid == 0 ? tile_bulk_src(p, tl, blockIdx.x) : nullptr;
+    if (ptid == 0 && bulk_cur) bulk_load(smp, bulk_cur, kSpanSamples * 2, bar_smp);
     int it = 0, n_bulk = 0;
-    while (cur.tile < n_tiles) {
-      const TileInfo nxt = next_tile<true>(p, cur.tile + gridDim.x, n_tiles, tiles_per_stream, lane);
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
+      const int b = it & 1;
       if (it > 0 && !mbar_wait(bar_a_free, (unsigned)(it - 1) & 1u)) break;
-      // ---- the tile's samples: smp[i] = frame (kt - 1) S + i ---------------------
-      if (cur.bulk) {
+      // ---- what the 64 window slots of this tile are ------------------------------
+      Slot* tile_slots = slots + (it % 3) * 64;
+      if (ptid < 64) {
+        tile_slots[ptid] = make_slot(p, tl, tile, ptid);
+        if (ptid == 0) *bulk_word = reinterpret_cast<unsigned long long>(bulk_cur);
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const bool bulk = *bulk_word != 0ULL;
+      // ---- the samples of the tile's runs ------------------------------------------
+      // bulk: smp[i] = frame (k0 - 1) S + i of the one stream; else run r of the tile at smp + r * run_samples
+      const int run_stride = bulk ? kGroupNew * kS : tl.run_samples;
+      if (bulk) {
         if (!mbar_wait(bar_smp, (unsigned)n_bulk & 1u)) break;
         n_bulk++;
       } else {
-        const Range rg = write_range(p.st.total, p.counts, p.frames, p.done, cur.s);
-        Source src;
-        src.channels = p.g.channels;
-        src.hist = p.hist + (size_t)cur.s * p.hist_stride;
-        src.in = p.in ? p.in + (size_t)cur.s * p.in_stride_frames * p.g.channels : nullptr;
-        src.hist_base = p.st.hist_base[cur.s];
-        src.t_old = rg.t_old;
-        src.t_new = rg.t_new;
-        stage_mono<256, short>(src, (long long)(cur.kt - 1) * kS, kTileSamples, rg.t_new, smp, nullptr, ptid);
+        for (int r = pwarp; r < kGroups * tl.runs_per_group; r += 8) {
+          const int g = r / tl.runs_per_group, r_local = r - g * tl.runs_per_group;
+          const Slot first = tile_slots[g * 16 + r_local * tl.slots_per_run];
+          bool any = false;
+          for (int q = 0; q < tl.slots_per_run; q++) any = any || (tile_slots[g * 16 + r_local * tl.slots_per_run + q].flags & 2);
+          if (!any) continue;
+          const Range rg = write_range(p.st.total, p.counts, p.frames, p.done, first.s);
+          Source src;
+          src.channels = p.g.channels;
+          src.hist = p.hist + (size_t)first.s * p.hist_stride;
+          src.in = p.in ? p.in + (size_t)first.s * p.in_stride_frames * p.g.channels : nullptr;
+          src.hist_base = p.st.hist_base[first.s];
+          src.t_old = rg.t_old;
+          src.t_new = rg.t_new;
+          stage_mono<32, short>(src, (long long)first.k * kS, tl.run_samples, rg.t_new, smp + r * tl.run_samples, nullptr, lane);
+        }
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
-      // ---- rows: unit = (chunk of eight t, window); consecutive threads take consecutive windows
+      // ---- rows: unit = (chunk of eight t, window slot); consecutive threads take consecutive slots
 #pragma unroll 1
       for (int u = ptid; u < 15 * 64; u += 256) {
         const int c = u >> 6, w = u & 63;
-        const int g = w >> 4, wl = w & 15;
-        const int wq = kGroupNew * g + wl;  // window kt - 1 + wq (wl = 0: the group's halo window)
-        const int k = cur.kt - 1 + wq;
+        const Slot sl = tile_slots[w];
         uint4 s_hi = make_uint4(0u, 0u, 0u, 0u), s_lo = s_hi, d_hi = s_hi, d_lo = s_hi;
-        if (k >= 0 && k < cur.kB) {
-          const short* x = smp + wq * kS;
+        if (sl.flags & 2) {
+          const short* x = smp + (sl.flags >> 16) * run_stride + ((sl.flags >> 8) & 0xff) * kS;
+          const int k = sl.k;
           const int nu = 120 + 8 * c, nl = 112 - 8 * c;  // first sample of the upper / lower eight
           const uint4 qu = *reinterpret_cast<const uint4*>(x + nu);
           const uint4 ql = *reinterpret_cast<const uint4*>(x + nl);
@@ -346,8 +402,8 @@ __global__ void __launch_bounds__(512, 1) k1_dft16(K1Params p, const uint4* __re
       if (ptid == 0) {
         bool ok = mbar_wait(bar_a_ready, (unsigned)it & 1u);
         // every row thread is done with the samples: the next tile's can start to arrive
-        if (ok && nxt.tile < n_tiles && nxt.bulk) bulk_load(smp, nxt.bulk, kTileSamples * 2, bar_smp);
-        const int b = it & 1;
+        bulk_cur = ok ? tile_bulk_src(p, tl, tile + gridDim.x) : nullptr;
+        if (bulk_cur) bulk_load(smp, bulk_cur, kSpanSamples * 2, bar_smp);
         if (ok && it >= 2) ok = mbar_wait(bar_acc_free + b, (unsigned)((it >> 1) - 1) & 1u);
         if (ok) {
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -368,11 +424,9 @@ __global__ void __launch_bounds__(512, 1) k1_dft16(K1Params p, const uint4* __re
         umma_commit(bar_a_free);
         umma_commit(bar_acc_full + b);
       }
-      cur = nxt;
-      it++;
     }
     // no bulk copy may still be in flight when the CTA retires
-    if (ptid == 0 && cur.tile < n_tiles && cur.bulk) mbar_wait(bar_smp, (unsigned)n_bulk & 1u);
+    if (ptid == 0 && bulk_cur) mbar_wait(bar_smp, (unsigned)n_bulk & 1u);
   } else {
     // =============================== epilogue =====================================
     // thread = accumulator row: lane pair (2 wl, 2 wl + 1) = (s-row, d'-row) of window wl of group `grp`;
@@ -383,16 +437,15 @@ __global__ void __launch_bounds__(512, 1) k1_dft16(K1Params p, const uint4* __re
     const int i0 = 61 * half;
     float2* xch = reinterpret_cast<float2*>(smem + kOffXch);  // [2 halves][4 groups][16 windows]: (energy, peak), then lsd
     int it = 0;
-    for (TileInfo ti = next_tile<false>(p, blockIdx.x, n_tiles, tiles_per_stream, lane); ti.tile < n_tiles;
-         ti = next_tile<false>(p, ti.tile + gridDim.x, n_tiles, tiles_per_stream, lane), it++) {
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
       const int b = it & 1;
       if (!mbar_wait(bar_acc_full + b, (unsigned)(it >> 1) & 1u)) break;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const unsigned row_base = tmem + ((unsigned)(grp * 32) << 16) + (unsigned)(b * kN);
-      const int k = ti.kt + kGroupNew * grp + wl - 1;
-      const bool out = wl >= 1 && k < ti.kB;
+      const Slot sl = slots[(it % 3) * 64 + grp * 16 + wl];
+      const bool out = (sl.flags & 1) != 0;
       float* tap = nullptr;
-      if (TAP && out) tap = p.tap_spec + ((size_t)ti.s * p.tap_stride + (k - ti.kA)) * 480;
+      if (TAP && out) tap = p.tap_spec + ((size_t)sl.s * p.tap_stride + (sl.k - sl.kA)) * 480;
       // pass 1: power and log2 power of this lane's bins; energy and peak (bins 0 and N/2 stay out of both)
       float l[64];
       float e = 0.0f, mx = 0.0f;
@@ -458,7 +511,7 @@ __global__ void __launch_bounds__(512, 1) k1_dft16(K1Params p, const uint4* __re
       asm volatile("bar.sync %0, 64;" ::"r"(2 + grp) : "memory");
       if (half == 0 && out && role == 0) {
         acc += xch[(4 + grp) * 16 + wl].x;
-        p.feat[(size_t)ti.s * p.feat_stride + (k - ti.kA)] = make_float2(e, acc * 0.34657359027997264f);  // ln2 / 2
+        p.feat[(size_t)sl.s * p.feat_stride + (sl.k - sl.kA)] = make_float2(e, acc * 0.34657359027997264f);  // ln2 / 2
       }
       asm volatile("bar.sync %0, 64;" ::"r"(2 + grp) : "memory");  // (the exchange slots are free for the next tile)
     }
@@ -472,7 +525,8 @@ __global__ void __launch_bounds__(512, 1) k1_dft16(K1Params p, const uint4* __re
 
 bool k1_dft16_supported(const K1Params& p) {
   const Geometry& g = p.g;
-  return g.fft == 480 && g.window == kW && g.step == kS && g.partial == kP && g.channels == 1;
+  // (any channel count: the mono down-mix of soniclib.c:271-274 happens while the samples are staged)
+  return g.fft == 480 && g.window == kW && g.step == kS && g.partial == kP && g.channels >= 1;
 }
 
 // C[t][j] = cos(2 pi j (t + 1/2) / 480) as fp16 hi + lo in operand layout (row = j, K = t), per device
@@ -515,11 +569,14 @@ cudaError_t launch_k1_dft16(const K1Params& p, cudaStream_t stream) {
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < kMaxDevices && sms[dev] == 0) cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
   const int n_sm = (dev >= 0 && dev < kMaxDevices && sms[dev] > 0) ? sms[dev] : 148;
-  const int tiles_per_stream = (p.max_new_frames + kTileNew - 1) / kTileNew;
-  const long long n_tiles = (long long)tiles_per_stream * p.n_streams;
-  const int grid = (int)(n_tiles < n_sm ? n_tiles : n_sm);
-  if (p.tap_spec) k1_dft16<true><<<grid, 512, kSmemBytes, stream>>>(p, dft, (int)n_tiles, tiles_per_stream);
-  else k1_dft16<false><<<grid, 512, kSmemBytes, stream>>>(p, dft, (int)n_tiles, tiles_per_stream);
+  // new windows per stream in this launch: at most one per step of new frames
+  long long n = (p.frames - p.done + kS - 1) / kS;
+  if (n > p.max_new_frames) n = p.max_new_frames;
+  if (n < 1) n = 1;
+  const Tiling tl = make_tiling((int)n, p.n_streams);
+  const int grid = tl.n_tiles < n_sm ? tl.n_tiles : n_sm;
+  if (p.tap_spec) k1_dft16<true><<<grid, 512, kSmemBytes, stream>>>(p, dft, tl);
+  else k1_dft16<false><<<grid, 512, kSmemBytes, stream>>>(p, dft, tl);
   count_launch();
   return cudaGetLastError();
 }

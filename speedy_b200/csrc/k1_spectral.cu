@@ -977,11 +977,13 @@ size_t k1_smem_bytes_480(int warps) {
 
 cudaError_t launch_k1(const K1Params& p, cudaStream_t stream) {
   if (p.max_new_frames <= 0) return cudaSuccess;
-  // 16 kHz mono writes of a second or more: the tensor-core shape (k1_dft16.cu), SPEEDY_K1_TC=0 turns it off
+  // 16 kHz mono: the tensor-core shape (k1_dft16.cu) for every launch, long or short, so that a
+  // stream's windows always go through the same arithmetic however its input is chunked;
+  // SPEEDY_K1_TC=0 selects the FFT kernel below instead
   {
     const char* e = getenv("SPEEDY_K1_TC");
     const int on = e ? atoi(e) : 1;
-    if (on && p.frames - p.done >= (long long)p.g.rate && k1_dft16_supported(p)) return launch_k1_dft16(p, stream);
+    if (on && k1_dft16_supported(p)) return launch_k1_dft16(p, stream);
   }
   K1Params q = p;
   q.runs_per_stream = (p.max_new_frames + kRun - 1) / kRun;
