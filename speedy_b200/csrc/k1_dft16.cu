@@ -23,15 +23,19 @@
 // same 1e-4 bars).  The accumulator holds 2^13 X; everything downstream works on log2 |X|^2
 // differences and on the energy, rescaled exactly (powers of two).
 //
-// Shape.  One persistent CTA per SM, 16 warps.  A tile is 64 window slots = 128 rows (2w: s,
+// Shape.  One persistent CTA per SM, 20 warps.  A tile is 64 window slots = 128 rows (2w: s,
 // 2w + 1: d'), four groups of 16; a group holds runs of consecutive windows of a stream, each a halo
 // window (the previous window, recomputed: its spectrum is the other operand of the spectral
 // difference) + up to 15 new ones: one long run, or several short ones of different streams (make_tiling).
-//   warps 8-15 prepare the rows: the tile's samples arrive in shared memory as one TMA bulk copy
-//              (cp.async.bulk + mbarrier, issued a tile ahead; tiles that touch the carried history
+//   warps 8-18 prepare the rows: the tile's samples arrive in shared memory as one TMA bulk copy
+//              (cp.async.bulk + mbarrier; tiles that touch the carried history or pack several streams
 //              are staged by the warps themselves), then pre-emphasis, window, fold and split into
-//              the A operand (no-swizzle canonical layout: core matrices of 8 rows x 16 bytes);
-//              one elected thread issues the 24 tcgen05.mma of the tile and commits to mbarriers;
+//              the A operand (no-swizzle canonical layout: core matrices of 8 rows x 16 bytes), one
+//              16-byte K chunk of a row pair per unit of work, each announced on the mbarrier of its
+//              MMA step;
+//   warp 19    one thread issues the 24 tcgen05.mma of a tile, step by step as the chunks land, and
+//              commits every step to a barrier that frees its chunks for the next tile's rows, so
+//              the rows of tile i + 1 are written under the MMAs of tile i;
 //   warps 0-7  read the accumulator (tcgen05.ld, thread = row, two warps per 32 rows with half of
 //              the columns each): lane pairs (s-row, d'-row) trade the mirrored columns by shuffle,
 //              each lane takes the bins of one side: power, log2, energy, 40 dB gate, spectral
@@ -51,25 +55,38 @@
 namespace speedy {
 
 __device__ int g_k1_dft16_error;
+#ifdef K1_TIMING
+// developer build: cycles per phase of CTA 0 (rows: 1 barrier, 2 samples, 3 units; issuer: 5 wait accumulator,
+// 6 wait chunks + MMA issue; epilogue: 8 wait accumulator, 9 pass 1, 10 exchange, 11 pass 2 + out; 15 tiles)
+__device__ unsigned long long g_k1_cycles[16];
+#define KT_DECL long long _kt = clock64()
+#define KT_MARK(slot, who) do { const long long _n = clock64(); if (blockIdx.x == 0 && (who)) atomicAdd(&g_k1_cycles[slot], (unsigned long long)(_n - _kt)); _kt = _n; } while (0)
+#else
+#define KT_DECL do {} while (0)
+#define KT_MARK(slot, who) do {} while (0)
+#endif
 
 namespace {
 
 constexpr int kS = 160, kW = 240, kP = 80;
 constexpr int kGroupNew = 15, kGroups = 4, kTileNew = kGroupNew * kGroups;  // 60 new windows per tile
 constexpr int kRows = 128, kK = 128, kN = 256;
+constexpr int kEpiWarps = 8, kRowWarps = 11;  // + one warp for the MMA issuer
+constexpr int kThreads = (kEpiWarps + kRowWarps + 1) * 32, kRowThreads = kRowWarps * 32;
 constexpr float kPreHi = 0.97f;                          // speedy.c:422
 constexpr float kPreLo = (float)(0.97 - (double)0.97f);  // remainder of the double constant
 
 // shared memory (bytes)
 constexpr int kOffBhi = 0, kOffBlo = 65536, kOffAhi = 131072, kOffAlo = 163840;
 constexpr int kOffWin = 196608;            // float[240]: Hamming / 4
-constexpr int kOffBars = kOffWin + 1024;   // 7 mbarriers
-constexpr int kOffSlot = kOffBars + 64;    // tensor-memory base address
+constexpr int kOffBars = kOffWin + 1024;   // 21 mbarriers
+constexpr int kOffSlot = kOffBars + 256;   // tensor-memory base address
 constexpr int kOffSamp = kOffSlot + 64;    // short[kSampCap]: the samples of the tile's runs
 constexpr int kSampCap = 12800;            // 32 runs of 400 (one new window + halo each) is the largest tile
 constexpr int kOffXch = kOffSamp + kSampCap * 2;       // float2[2][4][16]: the two column halves of a window meet here
-constexpr int kOffSlots = kOffXch + 2 * 4 * 16 * 8;    // Slot[3][64]: what each row pair of a tile is
-constexpr int kSmemBytes = kOffSlots + 3 * 64 * 16 + 16;
+constexpr int kOffSlots = kOffXch + 2 * 4 * 16 * 8;    // Slot[4][64]: what each row pair of a tile is
+constexpr int kOffBulk = kOffSlots + 4 * 64 * 16;      // int[4]: the tile's samples arrive as one bulk copy
+constexpr int kSmemBytes = kOffBulk + 16;
 constexpr int kSpanSamples = kTileNew * kS + kW;  // one stream's 61 consecutive windows: 9840 samples
 
 // element (r, k) of an [R x 128] K-major fp16 operand in the no-swizzle canonical layout: core
@@ -124,6 +141,10 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, unsigned parity) {
   return false;
 }
 // global -> shared bulk copy (TMA, 1-D), completion counted in bytes on `bar`
+// pull a span into L2 ahead of its bulk copy
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
@@ -244,36 +265,39 @@ __device__ __forceinline__ const int16_t* tile_bulk_src(const K1Params& p, const
 }  // namespace
 
 template <bool TAP>
-__global__ void __launch_bounds__(512, 1) k1_dft16(K1Params p, const uint4* __restrict__ dft_hi_lo, Tiling tl) {
+__global__ void __launch_bounds__(kThreads, 1) k1_dft16(K1Params p, const uint4* __restrict__ dft_hi_lo, Tiling tl) {
   extern __shared__ __align__(1024) unsigned char smem[];
   float* s_win = reinterpret_cast<float*>(smem + kOffWin);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
-  uint64_t* bar_a_ready = bars + 0;   // 256 arrivals: the rows of a tile are in shared memory
-  uint64_t* bar_a_free = bars + 1;    // commit: the MMAs that read them are done
-  uint64_t* bar_acc_full = bars + 2;  // [2] commit: accumulator b holds a tile
-  uint64_t* bar_acc_free = bars + 4;  // [2] 256 arrivals: the epilogue has read accumulator b (and the tile's slots)
-  uint64_t* bar_smp = bars + 6;       // bulk copy of a tile's samples has landed
+  uint64_t* bar_k_ready = bars + 0;    // [8] the two 8-element K chunks of MMA step ks are in shared memory (128 units; 64 for the last)
+  uint64_t* bar_k_free = bars + 8;     // [8] commit: the MMAs of step ks have read them
+  uint64_t* bar_acc_full = bars + 16;  // [2] commit: accumulator b holds a tile
+  uint64_t* bar_acc_free = bars + 18;  // [2] 256 arrivals: the epilogue has read accumulator b (and copied its slot)
+  uint64_t* bar_smp = bars + 20;       // bulk copy of a tile's samples has landed
   unsigned* tmem_slot = reinterpret_cast<unsigned*>(smem + kOffSlot);
-  unsigned long long* bulk_word = reinterpret_cast<unsigned long long*>(smem + kOffSlot + 16);  // this tile's bulk source (or 0)
   short* smp = reinterpret_cast<short*>(smem + kOffSamp);
-  // [3][64]: tile it uses table it % 3.  Three are enough without a barrier of their own: the rows of
-  // tile it are written after the MMAs of tile it - 1 have completed, and those were issued only after
-  // the epilogue of tile it - 3 had handed its accumulator back (it copies its slot first)
+  // [4][64]: tile it uses table it % 4.  Four are enough without a barrier of their own: the table of
+  // tile it + 1 is written while the rows of tile it are, i.e. after the MMAs of tile it - 1 have run, and
+  // those were issued only after the epilogue of tile it - 3 had handed its accumulator back (it copies
+  // its slot first)
   Slot* slots = reinterpret_cast<Slot*>(smem + kOffSlots);
+  int* bulk_flag = reinterpret_cast<int*>(smem + kOffBulk);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_tiles = tl.n_tiles;
 
   // the DFT matrix (hi, then lo), already in operand layout: 128 KB, once per CTA
   {
     uint4* dst = reinterpret_cast<uint4*>(smem + kOffBhi);
-    for (int i = tid; i < 131072 / 16; i += 512) dst[i] = dft_hi_lo[i];
+    for (int i = tid; i < 131072 / 16; i += kThreads) dst[i] = dft_hi_lo[i];
     uint4* a = reinterpret_cast<uint4*>(smem + kOffAhi);  // rows start as zeros (the K padding stays zero)
-    for (int i = tid; i < 65536 / 16; i += 512) a[i] = make_uint4(0u, 0u, 0u, 0u);
-    for (int i = tid; i < kW; i += 512) s_win[i] = p.window[i] * 0.25f;  // Hamming / 4: rows at the int16 scale / 4
+    for (int i = tid; i < 65536 / 16; i += kThreads) a[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < kW; i += kThreads) s_win[i] = p.window[i] * 0.25f;  // Hamming / 4: rows at the int16 scale / 4
   }
   if (tid == 0) {
-    mbar_init(bar_a_ready, 256);
-    mbar_init(bar_a_free, 1);
+    for (int ks = 0; ks < 8; ks++) {
+      mbar_init(bar_k_ready + ks, ks < 7 ? 128 : 64);  // (chunk 15 is the K padding: nobody writes it)
+      mbar_init(bar_k_free + ks, 1);
+    }
     mbar_init(bar_acc_full + 0, 1);
     mbar_init(bar_acc_full + 1, 1);
     mbar_init(bar_acc_free + 0, 256);
@@ -291,27 +315,66 @@ __global__ void __launch_bounds__(512, 1) k1_dft16(K1Params p, const uint4* __re
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const unsigned tmem = *tmem_slot;
 
-  if (warp >= 8) {
-    // =========================== rows + MMA issue ===============================
+  if (warp == kEpiWarps + kRowWarps) {
+    // ================================ MMA issue =====================================
+    // One thread: as soon as the two K chunks of a step are in shared memory it issues the step's three
+    // products and commits them to the step's "free" barrier, so the rows of the next tile are written
+    // under the MMAs of this one; after the last step it starts the next tile's bulk copy.
+    if (lane == 0) {
+      const unsigned idesc = (1u << 4) | ((unsigned)(kN >> 3) << 17) | ((unsigned)(kRows >> 4) << 24);  // f16 x f16 -> f32, K-major both
+      const unsigned ah = smem_u32(smem + kOffAhi), al = smem_u32(smem + kOffAlo);
+      const unsigned bh = smem_u32(smem + kOffBhi), bl = smem_u32(smem + kOffBlo);
+      const int16_t* first = tile_bulk_src(p, tl, blockIdx.x);
+      if (first) bulk_load(smp, first, kSpanSamples * 2, bar_smp);
+      int it = 0;
+      bool ok = true;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
+        const int b = it & 1;
+        KT_DECL;
+        // the next tile's samples start towards L2 now; its bulk copy follows when this tile's rows are done
+        const int16_t* nxt = tile_bulk_src(p, tl, tile + gridDim.x);
+        if (nxt) bulk_prefetch_l2(nxt, kSpanSamples * 2);
+        if (ok && it >= 2) ok = mbar_wait(bar_acc_free + b, (unsigned)((it >> 1) - 1) & 1u);
+        KT_MARK(5, true);
+        const unsigned acc = tmem + (unsigned)(b * kN);
+#pragma unroll 1
+        for (int ks = 0; ks < kK / 16; ks++) {  // two 8-element chunks per MMA
+          if (ok) ok = mbar_wait(bar_k_ready + ks, (unsigned)it & 1u);
+          if (ok) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const unsigned ao = (unsigned)ks * 2u * (kRows * 16), bo = (unsigned)ks * 2u * (kN * 16);
+            const uint64_t d_ah = make_desc(ah + ao, kRows * 16, 128), d_al = make_desc(al + ao, kRows * 16, 128);
+            const uint64_t d_bh = make_desc(bh + bo, kN * 16, 128), d_bl = make_desc(bl + bo, kN * 16, 128);
+            umma_f16(acc, d_ah, d_bh, idesc, ks > 0 ? 1u : 0u);
+            umma_f16(acc, d_al, d_bh, idesc, 1u);
+            umma_f16(acc, d_ah, d_bl, idesc, 1u);
+          }
+          umma_commit(bar_k_free + ks);  // (committed even after a time-out, so that the other roles drain too)
+        }
+        umma_commit(bar_acc_full + b);
+        KT_MARK(6, true);
+        // every row thread is done with the samples (all eight steps were ready): the next tile's can arrive
+        if (nxt && ok) bulk_load(smp, nxt, kSpanSamples * 2, bar_smp);
+#ifdef K1_TIMING
+        if (blockIdx.x == 0) atomicAdd(&g_k1_cycles[15], 1ULL);
+#endif
+      }
+    }
+  } else if (warp >= kEpiWarps) {
+    // ================================== rows =========================================
     const int ptid = tid - 256, pwarp = warp - 8;
     unsigned char* a_hi = smem + kOffAhi;
     unsigned char* a_lo = smem + kOffAlo;
-    const unsigned idesc = (1u << 4) | ((unsigned)(kN >> 3) << 17) | ((unsigned)(kRows >> 4) << 24);  // f16 x f16 -> f32, K-major both
-    // (thread 0 looks one tile ahead for the bulk copy)
-    const int16_t* bulk_cur = ptid == 0 ? tile_bulk_src(p, tl, blockIdx.x) : nullptr;
-    if (ptid == 0 && bulk_cur) bulk_load(smp, bulk_cur, kSpanSamples * 2, bar_smp);
+    if (ptid < 64) slots[ptid] = make_slot(p, tl, blockIdx.x, ptid);
+    if (ptid == 64) bulk_flag[0] = tile_bulk_src(p, tl, blockIdx.x) != nullptr;
     int it = 0, n_bulk = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
-      const int b = it & 1;
-      if (it > 0 && !mbar_wait(bar_a_free, (unsigned)(it - 1) & 1u)) break;
-      // ---- what the 64 window slots of this tile are ------------------------------
-      Slot* tile_slots = slots + (it % 3) * 64;
-      if (ptid < 64) {
-        tile_slots[ptid] = make_slot(p, tl, tile, ptid);
-        if (ptid == 0) *bulk_word = reinterpret_cast<unsigned long long>(bulk_cur);
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      const bool bulk = *bulk_word != 0ULL;
+      KT_DECL;
+      Slot* tile_slots = slots + (it & 3) * 64;
+      // (every row thread is done with the previous tile's samples; this tile's slot table is visible)
+      asm volatile("bar.sync 1, %0;" ::"n"(kRowThreads) : "memory");
+      KT_MARK(1, ptid == 32);
+      const bool bulk = bulk_flag[it & 3] != 0;
       // ---- the samples of the tile's runs ------------------------------------------
       // bulk: smp[i] = frame (k0 - 1) S + i of the one stream; else run r of the tile at smp + r * run_samples
       const int run_stride = bulk ? kGroupNew * kS : tl.run_samples;
@@ -319,7 +382,7 @@ __global__ void __launch_bounds__(512, 1) k1_dft16(K1Params p, const uint4* __re
         if (!mbar_wait(bar_smp, (unsigned)n_bulk & 1u)) break;
         n_bulk++;
       } else {
-        for (int r = pwarp; r < kGroups * tl.runs_per_group; r += 8) {
+        for (int r = pwarp; r < kGroups * tl.runs_per_group; r += kRowWarps) {
           const int g = r / tl.runs_per_group, r_local = r - g * tl.runs_per_group;
           const Slot first = tile_slots[g * 16 + r_local * tl.slots_per_run];
           bool any = false;
@@ -335,11 +398,13 @@ __global__ void __launch_bounds__(512, 1) k1_dft16(K1Params p, const uint4* __re
           src.t_new = rg.t_new;
           stage_mono<32, short>(src, (long long)first.k * kS, tl.run_samples, rg.t_new, smp + r * tl.run_samples, nullptr, lane);
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(kRowThreads) : "memory");
       }
+      KT_MARK(2, ptid == 32);
       // ---- rows: unit = (chunk of eight t, window slot); consecutive threads take consecutive slots
+      bool ok = true;
 #pragma unroll 1
-      for (int u = ptid; u < 15 * 64; u += 256) {
+      for (int u = ptid; u < 15 * 64; u += kRowThreads) {
         const int c = u >> 6, w = u & 63;
         const Slot sl = tile_slots[w];
         uint4 s_hi = make_uint4(0u, 0u, 0u, 0u), s_lo = s_hi, d_hi = s_hi, d_lo = s_hi;
@@ -390,43 +455,25 @@ __global__ void __launch_bounds__(512, 1) k1_dft16(K1Params p, const uint4* __re
           split2(dv[4], dv[5], d_hi.z, d_lo.z);
           split2(dv[6], dv[7], d_hi.w, d_lo.w);
         }
+        // the previous tile's MMAs of this K step have read the chunk
+        if (it > 0 && ok) ok = mbar_wait(bar_k_free + (c >> 1), (unsigned)(it - 1) & 1u);
         const int o = op_off(2 * w, 8 * c, kRows);  // (row 2w + 1 is the next 16 bytes)
         *reinterpret_cast<uint4*>(a_hi + o) = s_hi;
         *reinterpret_cast<uint4*>(a_hi + o + 16) = d_hi;
         *reinterpret_cast<uint4*>(a_lo + o) = s_lo;
         *reinterpret_cast<uint4*>(a_lo + o + 16) = d_lo;
+        // the tensor core reads shared memory through the async proxy
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(bar_k_ready + (c >> 1));
       }
-      // the tensor core reads shared memory through the async proxy
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_arrive(bar_a_ready);
-      if (ptid == 0) {
-        bool ok = mbar_wait(bar_a_ready, (unsigned)it & 1u);
-        // every row thread is done with the samples: the next tile's can start to arrive
-        bulk_cur = ok ? tile_bulk_src(p, tl, tile + gridDim.x) : nullptr;
-        if (bulk_cur) bulk_load(smp, bulk_cur, kSpanSamples * 2, bar_smp);
-        if (ok && it >= 2) ok = mbar_wait(bar_acc_free + b, (unsigned)((it >> 1) - 1) & 1u);
-        if (ok) {
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const unsigned acc = tmem + (unsigned)(b * kN);
-          const unsigned ah = smem_u32(a_hi), al = smem_u32(a_lo);
-          const unsigned bh = smem_u32(smem + kOffBhi), bl = smem_u32(smem + kOffBlo);
-#pragma unroll 1
-          for (int ks = 0; ks < kK / 16; ks++) {  // two 8-element chunks per MMA
-            const unsigned ao = (unsigned)ks * 2u * (kRows * 16), bo = (unsigned)ks * 2u * (kN * 16);
-            const uint64_t d_ah = make_desc(ah + ao, kRows * 16, 128), d_al = make_desc(al + ao, kRows * 16, 128);
-            const uint64_t d_bh = make_desc(bh + bo, kN * 16, 128), d_bl = make_desc(bl + bo, kN * 16, 128);
-            umma_f16(acc, d_ah, d_bh, idesc, ks > 0 ? 1u : 0u);
-            umma_f16(acc, d_al, d_bh, idesc, 1u);
-            umma_f16(acc, d_ah, d_bl, idesc, 1u);
-          }
-        }
-        // (committed even after a time-out, so that the other role drains too)
-        umma_commit(bar_a_free);
-        umma_commit(bar_acc_full + b);
+      KT_MARK(3, ptid == 32);
+      // the next tile's slot table, off the critical path
+      if (tile + gridDim.x < n_tiles) {
+        if (ptid < 64) slots[((it + 1) & 3) * 64 + ptid] = make_slot(p, tl, tile + gridDim.x, ptid);
+        if (ptid == 64) bulk_flag[(it + 1) & 3] = tile_bulk_src(p, tl, tile + gridDim.x) != nullptr;
       }
+      if (!ok) break;
     }
-    // no bulk copy may still be in flight when the CTA retires
-    if (ptid == 0 && bulk_cur) mbar_wait(bar_smp, (unsigned)n_bulk & 1u);
   } else {
     // =============================== epilogue =====================================
     // thread = accumulator row: lane pair (2 wl, 2 wl + 1) = (s-row, d'-row) of window wl of group `grp`;
@@ -439,10 +486,12 @@ __global__ void __launch_bounds__(512, 1) k1_dft16(K1Params p, const uint4* __re
     int it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
       const int b = it & 1;
+      KT_DECL;
       if (!mbar_wait(bar_acc_full + b, (unsigned)(it >> 1) & 1u)) break;
+      KT_MARK(8, tid == 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const unsigned row_base = tmem + ((unsigned)(grp * 32) << 16) + (unsigned)(b * kN);
-      const Slot sl = slots[(it % 3) * 64 + grp * 16 + wl];
+      const Slot sl = slots[(it & 3) * 64 + grp * 16 + wl];
       const bool out = (sl.flags & 1) != 0;
       float* tap = nullptr;
       if (TAP && out) tap = p.tap_spec + ((size_t)sl.s * p.tap_stride + (sl.k - sl.kA)) * 480;
@@ -480,6 +529,7 @@ __global__ void __launch_bounds__(512, 1) k1_dft16(K1Params p, const uint4* __re
       // the accumulator is in registers now: hand it back to the MMA issuer
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(bar_acc_free + b);
+      KT_MARK(9, tid == 0);
       // energy and peak of the window: the two roles by shuffle, the two halves through shared memory
       e += __shfl_xor_sync(0xffffffffu, e, 1);
       mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
@@ -490,6 +540,7 @@ __global__ void __launch_bounds__(512, 1) k1_dft16(K1Params p, const uint4* __re
         e = (e + o.x) * 1.4901161193847656e-08f;  // 2^-26: the /32768 scale of speedy.c:558
         mx = fmaxf(mx, o.y);
       }
+      KT_MARK(10, tid == 0);
       // pass 2, speedy.c:705-719 in the log2 domain: with n_i = |X_i| / (sqrt(E) + eps),
       //   log(n_c / n_l) = ln2 * (0.5 (lp_c - lp_l) + (linv_c - linv_l)),  lp = log2 |X|^2, linv = -log2(sqrt(E) + eps);
       //   |X_i| > max|X| / 100  <=>  lp_i > log2(max p) - log2(1e4)
@@ -514,6 +565,7 @@ __global__ void __launch_bounds__(512, 1) k1_dft16(K1Params p, const uint4* __re
         p.feat[(size_t)sl.s * p.feat_stride + (sl.k - sl.kA)] = make_float2(e, acc * 0.34657359027997264f);  // ln2 / 2
       }
       asm volatile("bar.sync %0, 64;" ::"r"(2 + grp) : "memory");  // (the exchange slots are free for the next tile)
+      KT_MARK(11, tid == 0);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -575,13 +627,23 @@ cudaError_t launch_k1_dft16(const K1Params& p, cudaStream_t stream) {
   if (n < 1) n = 1;
   const Tiling tl = make_tiling((int)n, p.n_streams);
   const int grid = tl.n_tiles < n_sm ? tl.n_tiles : n_sm;
-  if (p.tap_spec) k1_dft16<true><<<grid, 512, kSmemBytes, stream>>>(p, dft, tl);
-  else k1_dft16<false><<<grid, 512, kSmemBytes, stream>>>(p, dft, tl);
+  if (p.tap_spec) k1_dft16<true><<<grid, kThreads, kSmemBytes, stream>>>(p, dft, tl);
+  else k1_dft16<false><<<grid, kThreads, kSmemBytes, stream>>>(p, dft, tl);
   count_launch();
   return cudaGetLastError();
 }
 
 }  // namespace speedy
+
+#ifdef K1_TIMING
+extern "C" void speedyDebugK1Cycles(unsigned long long* out, int reset) {
+  if (out) cudaMemcpyFromSymbol(out, speedy::g_k1_cycles, sizeof(unsigned long long) * 16);
+  if (reset) {
+    unsigned long long z[16] = {0};
+    cudaMemcpyToSymbol(speedy::g_k1_cycles, z, sizeof(z));
+  }
+}
+#endif
 
 extern "C" int speedyDebugK1Dft16Error(void) {
   int v = 0;
