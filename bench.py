@@ -418,7 +418,7 @@ def run_cuda_arm(args):
         roofline = {
             "bound": "hbm", "kernel": "k4_sonic" if dominant == "sonic" else ("k1_spectral_480" if RATE == 16000 else "k1_spectral_mixed"),
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": ncu_traffic("k4_sonic" if dominant == "sonic" else "k1_spectral") if CFG["number"] == 2 and n == 1024 and SECONDS == 60 else None,
+            "traffic": ncu_traffic("k4_sonic" if dominant == "sonic" else "k1_") if CFG["number"] == 2 and n == 1024 and SECONDS == 60 else None,
             "traffic_source": "profiles/%s (ncu --set full, one launch per step)" % NCU_SUMMARY,
             "peak_source": peak_src,
             "algorithmic_bytes_per_launch": alg[dominant], "kernel_ms": dom_ms,

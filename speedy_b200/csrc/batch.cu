@@ -912,6 +912,14 @@ int speedyBatchWriteDevice(speedyBatch b, const int16_t* d_in, int64_t stride_fr
   int parts = 1;
   if (frames >= 8LL * b->g.rate) parts = 6;       // >= 8 s of audio per stream
   else if (frames >= 2LL * b->g.rate) parts = 3;
+  if (k1_uses_dft16(b->g)) {
+    // the tensor-core analysis kernel does not share SMs with the resynthesis (it fills an SM's shared
+    // memory), so prefixes only pay while the resynthesis leaves SMs idle: three at the latency-bound
+    // stream counts (measured 16.8 ms against 17.4 with six and 17.4 with one at 1024 x 60 s), one when
+    // the streams fill the machine (54.9 ms against 57.0 with six at 8192 x 30 s)
+    if (parts > 3) parts = 3;
+    if (b->n >= 148 * 24) parts = 1;
+  }
   if (const char* e = getenv("SPEEDY_B200_WRITE_PARTS")) parts = atoi(e) > 0 ? atoi(e) : parts;
   if (parts > kPipeEvents - 2) parts = kPipeEvents - 2;
   if (parts == 1) {

@@ -975,15 +975,23 @@ size_t k1_smem_bytes_480(int warps) {
   return 240 * sizeof(float) + 240 * sizeof(float2) + (size_t)warps * sizeof(WarpSmem480);
 }
 
+// Does launch_k1 take the tensor-core kernel for this geometry?  (It occupies an SM's shared memory
+// alone, so the analysis no longer shares SMs with the resynthesis kernel: the write pipeline in
+// batch.cu cuts long writes into fewer prefixes then.)
+bool k1_uses_dft16(const Geometry& g) {
+  const char* e = getenv("SPEEDY_K1_TC");
+  K1Params q;
+  q.g = g;
+  return (e ? atoi(e) : 1) != 0 && k1_dft16_supported(q);
+}
+
 cudaError_t launch_k1(const K1Params& p, cudaStream_t stream) {
   if (p.max_new_frames <= 0) return cudaSuccess;
   // 16 kHz mono: the tensor-core shape (k1_dft16.cu) for every launch, long or short, so that a
   // stream's windows always go through the same arithmetic however its input is chunked;
   // SPEEDY_K1_TC=0 selects the FFT kernel below instead
   {
-    const char* e = getenv("SPEEDY_K1_TC");
-    const int on = e ? atoi(e) : 1;
-    if (on && k1_dft16_supported(p)) return launch_k1_dft16(p, stream);
+    if (k1_uses_dft16(p.g)) return launch_k1_dft16(p, stream);
   }
   K1Params q = p;
   q.runs_per_stream = (p.max_new_frames + kRun - 1) / kRun;
