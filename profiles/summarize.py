@@ -46,8 +46,10 @@ def main():
     tag, rep, launches, *bench = sys.argv[1:]
     command = os.environ.get("SUMMARIZE_COMMAND") or (
         "SPEEDY_B200_WRITE_PARTS=1 ncu --set full --clock-control none --import-source on "
-        "-k regex:'k4_sonic|k1_spectral|k2_tension' --launch-skip 12 --launch-count 4 python bench.py --steps 1 --warmup 3")
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        "-k regex:'k4_sonic|k1_dft16|k2_tension' --launch-skip 6 --launch-count 4 python bench.py --steps 1 --warmup 3")
+    # (a report, or the `ncu -i report --page raw --csv` export of one made on the GPU box: the reports
+    # themselves can be too large to bring back)
+    raw = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
     ix = {h: i for i, h in enumerate(hdr)}
@@ -63,7 +65,7 @@ def main():
                 k[name + "_unit"] = units[ix[m]]
         kernels.append(k)
     json.dump({"source": os.path.basename(rep), "command": command, "kernels": kernels},
-              open(os.path.join(HERE, tag + "_kernels.json"), "w"), indent=1)
+              open(os.path.join(HERE, tag + os.environ.get("SUMMARIZE_SUFFIX", "_kernels") + ".json"), "w"), indent=1)
     if launches == "-":  # a kernel capture only
         print(json.dumps([{k: v for k, v in kk.items() if not k.endswith("_unit")} for kk in kernels], indent=1)[:3000])
         return

@@ -177,6 +177,13 @@ __device__ __forceinline__ void tmem_ld16(unsigned taddr, float (&v)[16]) {
   for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
 }
 
+// log2 on the special-function unit alone (the powers here are never subnormal unless they are zero)
+__device__ __forceinline__ float fast_log2(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // x = hi + lo with hi on an fp16 grid (top 11 bits, by truncation: exact) and lo the exact
 // remainder rounded to fp16; two values per call, packed as half2 bit patterns
 __device__ __forceinline__ void split2(float a, float b, unsigned& hi, unsigned& lo) {
@@ -511,8 +518,13 @@ __global__ void __launch_bounds__(kThreads, 1) k1_dft16(K1Params p, const uint4*
           // the partner's column 240 - i: Re and Im of the same bin meet here
           const float other = __shfl_xor_sync(0xffffffffu, hi[15 - j], 1);
           const float q = __fmaf_rn(lo[j], lo[j], __fmul_rn(other, other));  // 2^26 |X|^2
-          l[ii] = __log2f(q);
-          const bool counted = i >= 1 && i <= 120 && (i < 120 || role == 0);  // (i = 121 only pads the upper half)
+          l[ii] = fast_log2(q);
+          // bins 0 (ii = 0 of the lower half) and N/2 stay out; bin 120 counts once (role 0); ii = 60 of the
+          // upper half (i = 121) is padding: only these three positions need a test
+          bool counted = true;
+          if (ii == 0) counted = half != 0;
+          if (ii == 59) counted = half == 0 || role == 0;
+          if (ii == 60) counted = half == 0;
           const float qc = counted ? q : 0.0f;
           e += qc;
           mx = fmaxf(mx, qc);
@@ -544,17 +556,20 @@ __global__ void __launch_bounds__(kThreads, 1) k1_dft16(K1Params p, const uint4*
       // pass 2, speedy.c:705-719 in the log2 domain: with n_i = |X_i| / (sqrt(E) + eps),
       //   log(n_c / n_l) = ln2 * (0.5 (lp_c - lp_l) + (linv_c - linv_l)),  lp = log2 |X|^2, linv = -log2(sqrt(E) + eps);
       //   |X_i| > max|X| / 100  <=>  lp_i > log2(max p) - log2(1e4)
-      const float linv = -__log2f(__fsqrt_rn(e) + 2.2204e-16f);
+      const float linv = -fast_log2(__fsqrt_rn(e) + 2.2204e-16f);
       const float linv_last = __shfl_up_sync(0xffffffffu, linv, 2);
-      const float thr = __log2f(mx) - 13.287712379549449f;
+      const float thr = fast_log2(mx) - 13.287712379549449f;
       const float d2 = 2.0f * (linv - linv_last);
       float acc = 0.0f;
 #pragma unroll
       for (int ii = 0; ii <= 60; ii++) {
-        const int i = i0 + ii;
         const float ll = __shfl_up_sync(0xffffffffu, l[ii], 2);  // the same bin of the previous window
         const float term = fabsf((l[ii] - ll) + d2);
-        if (i >= 1 && i <= 120 && (i < 120 || role == 0) && l[ii] > thr && ll > thr) acc += term;
+        bool counted = true;  // (as in pass 1)
+        if (ii == 0) counted = half != 0;
+        if (ii == 59) counted = half == 0 || role == 0;
+        if (ii == 60) counted = half == 0;
+        if (counted && l[ii] > thr && ll > thr) acc += term;
       }
       acc += __shfl_xor_sync(0xffffffffu, acc, 1);
       asm volatile("bar.sync %0, 64;" ::"r"(2 + grp) : "memory");  // (both halves have read the energies)
