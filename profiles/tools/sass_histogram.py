@@ -15,7 +15,7 @@ for line in txt.split("\n"):
     m = re.match(r"\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_]*)", line)
     if m and fn:
         hist[fn][m.group(1)] += 1
-special = ["UBLKCP", "UTMALDG", "UTMASTG", "SYNCS", "LDGSTS", "UTCHMMA", "UTCQMMA", "UTCBAR", "LDTM", "STTM", "REDUX", "CREDUX", "VABSDIFF", "IDP"]
+special = ["UBLKCP", "UBLKPF", "UTMALDG", "UTMASTG", "SYNCS", "LDGSTS", "UTCHMMA", "UTCQMMA", "UTCBAR", "UTCATOMSWS", "LDTM", "STTM", "REDUX", "CREDUX", "VABSDIFF", "IDP"]
 out = {"library": lib, "kernels": {}, "totals": collections.Counter()}
 for k, c in sorted(hist.items()):
     out["kernels"][k] = {"instructions": sum(c.values()), "top": dict(c.most_common(12)),

@@ -447,7 +447,8 @@ const char* speedyBatchLastError(void) { return g_error.c_str(); }
 int64_t speedyBatchKernelLaunches(void) { return g_launches.load(); }
 
 const char* speedyBatchBuildInfo(void) {
-  return "speedy_b200 sm_100a: k1_spectral_480<4 warps> (radix-8 x radix-15 real FFT) | "
+  return "speedy_b200 sm_100a: k1_dft16 (16 kHz spectrogram as a tcgen05 GEMM, TMEM accumulator, TMA-fed) | "
+         "k1_spectral_480<4 warps> (radix-8 x radix-15 real FFT, SPEEDY_K1_TC=0) | "
          "k1_spectral_mixed<128> (packed half-length Stockham FFT, any even window) | k1_spectral_bluestein<128> (chirp-z, "
          "prime windows) | "
          "k2_tension | k4_sonic<1|2|4 warps per stream, mono specialisation> | tail | read | synth";
