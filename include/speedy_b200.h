@@ -268,9 +268,10 @@ int speedyBatchPeekOutputDevice(speedyBatch batch, const int16_t** d_out,
 /* Drop the pending output of every stream without copying it. */
 int speedyBatchDiscardOutput(speedyBatch batch, void* cuda_stream);
 
-/* One-shot convenience over host buffers: write `frames` per stream, flush,
- * read; host<->device copies are pipelined against the kernels in slabs of
- * streams.  out_counts[s] receives the frames produced.  Return 1/0. */
+/* One-shot convenience over host buffers: RESET (every stream starts empty: state and
+ * pending output of earlier calls are discarded; parameters are kept), write `frames`
+ * per stream, flush, read; host<->device copies are pipelined against the kernels in
+ * chunks of time.  out_counts[s] receives the frames produced.  Return 1/0. */
 int speedyBatchProcess(speedyBatch batch, const int16_t* h_in, int64_t frames,
                        int16_t* h_out, int64_t out_stride_frames,
                        int32_t* h_out_counts);
@@ -293,7 +294,9 @@ int speedyBatchGetTaps(speedyBatch batch, int64_t max_frames,
                        float* spectrogram, float* energy, float* features,
                        float* tension, float* speed);
 
-/* Per-stream status bits (host array of num_streams). */
+/* Per-stream status bits (host array of num_streams).  Ordering contract of the host-side
+ * helpers (GetStatus, GetTaps, SetSpeed / SetNonlinear / SetFeedback with a host array): they
+ * wait for ALL work queued on the device, including *Device calls on a caller's stream. */
 #define SPEEDY_STATUS_OUTPUT_OVERFLOW 1 /* output did not fit out_capacity */
 #define SPEEDY_STATUS_FLUSHED 2
 #define SPEEDY_STATUS_INPUT_OVERFLOW 4  /* Sonic FIFO outgrew the history */

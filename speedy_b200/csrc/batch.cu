@@ -402,6 +402,8 @@ bool dev_alloc(speedyBatch b, T** p, size_t count) {
 cudaStream_t pick_stream(speedyBatch b, void* s) { return s ? (cudaStream_t)s : b->own_stream; }
 
 int fill_floats(speedyBatch b, float* d, const float* values, float uniform, cudaStream_t st) {
+  // parameters change between launches, never under one: kernels queued on a caller's stream finish first
+  CU_TRY(cudaDeviceSynchronize());
   if (values) {
     CU_TRY(cudaMemcpyAsync(d, values, sizeof(float) * b->n, cudaMemcpyHostToDevice, st));
     CU_TRY(cudaStreamSynchronize(st));
@@ -907,6 +909,10 @@ int speedyBatchWriteDevice(speedyBatch b, const int16_t* d_in, int64_t stride_fr
     return 0;
   }
   if (frames == 0) return 1;
+  if (!d_in || stride_frames < frames) {
+    set_error("speedyBatchWriteDevice: null input or stride_frames < frames");
+    return 0;
+  }
   CU_TRY(cudaSetDevice(b->cfg.device));
   cudaStream_t st = pick_stream(b, cuda_stream);
   WriteCall w = {b, d_in, stride_frames, frames, d_counts};
@@ -1375,7 +1381,7 @@ int speedyBatchProcess(speedyBatch b, const int16_t* h_in, int64_t frames, int16
 int speedyBatchGetStatus(speedyBatch b, int32_t* status) {
   if (!b || !status) return 0;
   CU_TRY(cudaSetDevice(b->cfg.device));
-  CU_TRY(cudaStreamSynchronize(b->own_stream));
+  CU_TRY(cudaDeviceSynchronize());  // (work may be queued on a caller's stream as well as on ours)
   CU_TRY(cudaMemcpy(status, b->st.status, sizeof(int32_t) * b->n, cudaMemcpyDeviceToHost));
   return 1;
 }

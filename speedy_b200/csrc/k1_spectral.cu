@@ -129,12 +129,6 @@ __device__ __forceinline__ float warp_max(float v) {
   return __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(v)));
 }
 
-// speedy.c:641-642: inverse_norm = 1.0 / (sqrt(energy) + eps), double, stored float.
-__device__ __forceinline__ float inverse_norm(float energy) {
-  const float eps = 2.2204e-16f;
-  return (float)(1.0 / (sqrt((double)energy) + (double)eps));
-}
-
 // ---------------------------------------------------------------------------
 // 16 kHz fast path
 // ---------------------------------------------------------------------------

@@ -8,6 +8,7 @@
     BASELINE.json configuration (recorded under profiles/ when SPEEDY_RECORD_PARITY is set);
   * element-wise relative error (with a stated absolute floor) beside the scale-relative bar.
 """
+import ctypes as C
 import json
 import os
 
@@ -265,3 +266,47 @@ def test_elementwise_relative_error(golden_inputs):
     assert np.all(np.abs(sp - spo) <= 1e-4 * np.abs(spo))
     print("element-wise: spectrogram (bins above -60 dB) %.2e, tension abs %.2e, speed rel %.2e"
           % (rel_loud, float(np.max(np.abs(t - to))), float(np.max(np.abs(sp - spo) / np.abs(spo)))))
+
+
+def test_tensor_core_spectrogram_equals_fft_kernel():
+    """The 16 kHz spectrogram as a tcgen05 GEMM (k1_dft16.cu, the default) against the FFT kernel
+    (k1_spectral_480, SPEEDY_K1_TC=0) on the same streams: every tap within 1e-5 of the other's scale
+    (measured 2.5e-6: split-fp16 products carry ~2^-21 per term), in long writes (one stream per tile,
+    bulk-copied samples), 10 ms chunks (32 streams per tile, staged samples), ragged stream lengths and
+    stereo (down-mix while staging); a silent and a very quiet stream included."""
+    n, rate, frames = 6, 16000, 16000 * 4
+    pcm = ol.synth(11, n, rate, 1, frames)
+    pcm[1, :5000] = 0
+    pcm[2] = (pcm[2].astype(np.int32) // 64).astype(np.int16)
+    stereo = ol.synth(12, 3, rate, 2, frames // 2)
+    cases = [("one write", pcm, dict()), ("10 ms chunks", pcm[:, :16000], dict(chunk=160)),
+             ("ragged", pcm, dict(counts=[frames, frames - 777, 300, 0, frames // 2, 1234])), ("stereo", stereo, dict(chunk=4000))]
+    old = os.environ.get("SPEEDY_K1_TC")
+    try:
+        for name, x, kw in cases:
+            res = {}
+            for tc in ("0", "1"):
+                os.environ["SPEEDY_K1_TC"] = tc
+                res[tc] = gpu_process(x, rate, 2.0, **kw)
+            a, b = res["0"][1], res["1"][1]
+            for key in ("spectrogram", "energy", "features", "tension", "speed"):
+                for s in range(x.shape[0]):
+                    u, v = a[key][s].astype(np.float64), b[key][s].astype(np.float64)
+                    assert u.shape == v.shape, (name, key, s)
+                    if u.size == 0:
+                        continue
+                    if key == "spectrogram":
+                        d = (np.abs(u - v) / np.maximum(u.max(axis=1, keepdims=True), 1e-30)).max()
+                    elif key == "features":
+                        d = (np.abs(u - v) / np.maximum(np.abs(u).max(axis=0, keepdims=True), 1e-30)).max()
+                    else:
+                        d = np.abs(u - v).max() / max(np.abs(u).max(), 1e-30)
+                    assert d < 1e-5, (name, key, s, d)
+    finally:
+        if old is None:
+            os.environ.pop("SPEEDY_K1_TC", None)
+        else:
+            os.environ["SPEEDY_K1_TC"] = old
+    L = sb.lib()
+    L.speedyDebugK1Dft16Error.restype = C.c_int
+    assert L.speedyDebugK1Dft16Error() == 0  # no barrier of the kernel ever timed out
