@@ -154,7 +154,22 @@ struct Sonic {
     const long long room = cap * nch() - base;
     short* o = out + base;
     T_BEGIN();
-    if (nch() == 1) {
+    if (nch() == 1 && NW == 1 && fold_all) {
+      // one warp, few streams per SM (latency bound): up to 128 frames as four independent slots (all loads first, then the stores), the
+      // rest -- rare -- in a loop; a lone warp otherwise waits out a shared-memory round trip per 32 frames
+      const int* src = w32 + o0 + vl;
+      int v[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) v[q] = vl + 32 * q < total ? src[32 * q] : 0;
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const int i = vl + 32 * q;
+        if (i < total && i < room) o[i] = (short)v[q];
+      }
+      for (int i = 128 + vl; i < total; i += 32) {
+        if (i < room) o[i] = (short)w32[o0 + i];
+      }
+    } else if (nch() == 1) {
       for (int i = vl; i < total; i += VL) {
         if (i < room) o[i] = (short)w32[o0 + i];
       }
@@ -194,6 +209,30 @@ struct Sonic {
     if (nch() == 1) {
       if (n == 1) {
         if (vl == 0 && 0 < room) o[0] = (short)w32[d0];
+      } else if (NW == 1 && fold_all) {
+        // (as in emit_copy: four independent slots, loads first; the many-stream shapes keep the loop:
+        // 8192 x 30 s measured 39.2 ms with the slots against 38.9 with it)
+        const int* dp = w32 + d0 + vl;
+        const int* up = w32 + u0 + vl;
+        int a[4], b[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const bool in = vl + 32 * q < total;
+          a[q] = in ? dp[32 * q] : 0;
+          b[q] = in ? up[32 * q] : 0;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const int t = vl + 32 * q;
+          const int num = a[q] * (n - t) + b[q] * t;
+          const int qq = (int)(__umulhi((unsigned)abs(num), magic) >> shift);
+          if (t < total && t < room) o[t] = (short)(num < 0 ? -qq : qq);
+        }
+        for (int t = 128 + vl; t < total; t += 32) {
+          const int num = w32[d0 + t] * (n - t) + w32[u0 + t] * t;
+          const int qq = (int)(__umulhi((unsigned)abs(num), magic) >> shift);
+          if (t < room) o[t] = (short)(num < 0 ? -qq : qq);
+        }
       } else {
         for (int t = vl; t < total; t += VL) {
           const int num = w32[d0 + t] * (n - t) + w32[u0 + t] * t;
