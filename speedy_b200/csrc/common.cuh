@@ -83,7 +83,9 @@ __device__ __forceinline__ void stage_frame(const int16_t* p, int C, T* dst, sho
 // Frames [a, b) of one contiguous source (ptr[0] is the first sample of frame f0) into
 // dst[f - start]: 16-byte loads (8 int16, four in flight per thread) over the part
 // that is 16-byte aligned in the source, one frame at a time at its ragged ends.
-template <int THREADS, typename T>
+// INFLIGHT: 16-byte loads a thread issues before it consumes the first (a lone warp on a latency-bound
+// chain asks for 16: a whole 4096-frame window in one round trip to HBM instead of four).
+template <int THREADS, typename T, int INFLIGHT = 4>
 __device__ __forceinline__ void stage_span(const int16_t* ptr, long long f0, int C, long long a, long long b,
                                            long long start, T* dst, short* raw16, int tid) {
   if (b <= a) return;
@@ -100,15 +102,15 @@ __device__ __forceinline__ void stage_span(const int16_t* ptr, long long f0, int
       T* d = dst + (fv0 - start);
       const bool d_aligned = (reinterpret_cast<size_t>(d) & 15) == 0;
       short* r = raw16 ? raw16 + (fv0 - start) * C : nullptr;
-      for (int vb = tid; vb < nvec; vb += 4 * THREADS) {
-        int4 q4[4];
+      for (int vb = tid; vb < nvec; vb += INFLIGHT * THREADS) {
+        int4 q4[INFLIGHT];
 #pragma unroll
-        for (int u = 0; u < 4; u++) {  // four 16-byte loads in flight per thread
+        for (int u = 0; u < INFLIGHT; u++) {  // INFLIGHT 16-byte loads in flight per thread
           const int v = vb + u * THREADS;
           q4[u] = v < nvec ? vp[v] : make_int4(0, 0, 0, 0);
         }
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
+        for (int u = 0; u < INFLIGHT; u++) {
           const int v = vb + u * THREADS;
           if (v >= nvec) continue;
           const int w[4] = {q4[u].x, q4[u].y, q4[u].z, q4[u].w};
@@ -160,7 +162,7 @@ __device__ __forceinline__ void stage_span(const int16_t* ptr, long long f0, int
 // outside [src.hist_base, lim) read as 0.  The carried history and the caller's
 // buffer are each one contiguous span.  raw16 (optional, channels > 1) receives the
 // interleaved samples too.
-template <int THREADS, typename T>
+template <int THREADS, typename T, int INFLIGHT = 4>
 __device__ __forceinline__ void stage_mono(const Source& src, long long start, int count, long long lim,
                                            T* dst, short* raw16, int tid) {
   const int C = src.channels;
@@ -175,7 +177,7 @@ __device__ __forceinline__ void stage_mono(const Source& src, long long start, i
   long long i1 = end < lim ? end : lim;
   if (i1 < i0) i1 = i0;
   stage_span<THREADS, T>(src.hist, src.hist_base, C, h0, h1, start, dst, raw16, tid);
-  if (src.in) stage_span<THREADS, T>(src.in, src.t_old, C, i0, i1, start, dst, raw16, tid);
+  if (src.in) stage_span<THREADS, T, INFLIGHT>(src.in, src.t_old, C, i0, i1, start, dst, raw16, tid);
   // zeros: before the history begins, and from the end of the data on
   const long long z0 = h0 < end ? h0 : end;                        // [start, z0)
   const long long z1 = (src.in && i1 > i0) ? i1 : (h1 > start ? h1 : start);  // [z1, end)

@@ -34,6 +34,15 @@ __global__ void __launch_bounds__(kWarps * 32) k2_tension(K2Params p, float alph
   __shared__ float s_comp[kWarps][kSmemRing];
   __shared__ float s_energy[kWarps][kSmemRing];
   __shared__ float s_lsd[kWarps][kSmemRing];
+  // the hysteresis triangles (speedy.c:590-610): (F - i) / F and (B - i) / B, the same correctly rounded
+  // quotients the per-tap divisions gave, computed once instead of 34 times per frame
+  __shared__ float s_tri_f[32], s_tri_b[32];
+  if (threadIdx.x < 32) {
+    const int i = threadIdx.x;
+    s_tri_f[i] = i <= p.g.future ? __fdiv_rn((float)(p.g.future - i), (float)p.g.future) : 0.0f;
+    s_tri_b[i] = i <= p.g.past ? __fdiv_rn((float)(p.g.past - i), (float)p.g.past) : 0.0f;
+  }
+  __syncthreads();
 
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -132,13 +141,13 @@ __global__ void __launch_bounds__(kWarps * 32) k2_tension(K2Params p, float alph
       for (int i = 0; i <= F; i++) {
         const int t = r + i;
         float v = t >= g.time_base ? rc[t & (kSmemRing - 1)] : 0.0f;
-        v = __fmul_rn(v, __fdiv_rn((float)(F - i), (float)F));
+        v = __fmul_rn(v, s_tri_f[i]);
         if (v > future_max) future_max = v;
       }
       for (int i = 0; i <= B; i++) {
         const int t = r - i;
         float v = t >= g.time_base ? rc[t & (kSmemRing - 1)] : 0.0f;
-        v = __fmul_rn(v, __fdiv_rn((float)(B - i), (float)B));
+        v = __fmul_rn(v, s_tri_b[i]);
         if (v > past_max) past_max = v;
       }
       hyst = __fmul_rn(__fadd_rn(past_max, future_max), 0.5f);

@@ -131,7 +131,8 @@ struct Sonic {
     sync();  // every lane is done with the old window
     bufStart = start & ~7LL;  // keeps the 16-byte loads of the refill aligned
     bufLen = bufN;
-    stage_mono<VL, int>(src, bufStart, bufN, zero_from, w32, nch() > 1 ? buf : nullptr, vl);
+    if (NW == 1 && CH == 1 && fold_all) stage_mono<VL, int, 16>(src, bufStart, bufN, zero_from, w32, nullptr, vl);
+    else stage_mono<VL, int>(src, bufStart, bufN, zero_from, w32, nch() > 1 ? buf : nullptr, vl);
     sync();
     T_END(0);
   }
