@@ -921,10 +921,11 @@ int speedyBatchWriteDevice(speedyBatch b, const int16_t* d_in, int64_t stride_fr
   else if (frames >= 2LL * b->g.rate) parts = 3;
   if (k1_uses_dft16(b->g)) {
     // the tensor-core analysis kernel does not share SMs with the resynthesis (it fills an SM's shared
-    // memory), so prefixes only pay while the resynthesis leaves SMs idle: three at the latency-bound
-    // stream counts (measured 16.8 ms against 17.4 with six and 17.4 with one at 1024 x 60 s), one when
-    // the streams fill the machine (54.9 ms against 57.0 with six at 8192 x 30 s)
-    if (parts > 3) parts = 3;
+    // memory), so prefixes only pay while the resynthesis leaves SMs idle: four at the latency-bound
+    // stream counts (measured 15.6 ms against 15.7 with three or six and 15.9 with one at 1024 x 60 s;
+    // giving the analysis of a later prefix a few SMs of its own beside the resynthesis: 16.8 - 19.9 ms),
+    // one when the streams fill the machine (54.9 ms against 57.0 with six at 8192 x 30 s)
+    if (parts > 4) parts = 4;
     if (b->n >= 148 * 24) parts = 1;
   }
   if (const char* e = getenv("SPEEDY_B200_WRITE_PARTS")) parts = atoi(e) > 0 ? atoi(e) : parts;
