@@ -79,7 +79,7 @@ constexpr float kPreLo = (float)(0.97 - (double)0.97f);  // remainder of the dou
 // shared memory (bytes)
 constexpr int kOffBhi = 0, kOffBlo = 65536, kOffAhi = 131072, kOffAlo = 163840;
 constexpr int kOffWin = 196608;            // float[240]: Hamming / 4
-constexpr int kOffBars = kOffWin + 1024;   // 21 mbarriers
+constexpr int kOffBars = kOffWin + 1024;   // 22 mbarriers
 constexpr int kOffSlot = kOffBars + 256;   // tensor-memory base address
 constexpr int kOffSamp = kOffSlot + 64;    // short[kSampCap]: the samples of the tile's runs
 constexpr int kSampCap = 12800;            // 32 runs of 400 (one new window + halo each) is the largest tile
@@ -281,6 +281,7 @@ __global__ void __launch_bounds__(kThreads, 1) k1_dft16(K1Params p, const uint4*
   uint64_t* bar_acc_full = bars + 16;  // [2] commit: accumulator b holds a tile
   uint64_t* bar_acc_free = bars + 18;  // [2] 256 arrivals: the epilogue has read accumulator b (and copied its slot)
   uint64_t* bar_smp = bars + 20;       // bulk copy of a tile's samples has landed
+  uint64_t* bar_smp_free = bars + 21;  // every row thread holds its share of the tile's samples in registers
   unsigned* tmem_slot = reinterpret_cast<unsigned*>(smem + kOffSlot);
   short* smp = reinterpret_cast<short*>(smem + kOffSamp);
   // [4][64]: tile it uses table it % 4.  Four are enough without a barrier of their own: the table of
@@ -310,6 +311,7 @@ __global__ void __launch_bounds__(kThreads, 1) k1_dft16(K1Params p, const uint4*
     mbar_init(bar_acc_free + 0, 256);
     mbar_init(bar_acc_free + 1, 256);
     mbar_init(bar_smp, 1);
+    mbar_init(bar_smp_free, kRowThreads);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -333,6 +335,7 @@ __global__ void __launch_bounds__(kThreads, 1) k1_dft16(K1Params p, const uint4*
       const unsigned bh = smem_u32(smem + kOffBhi), bl = smem_u32(smem + kOffBlo);
       const int16_t* first = tile_bulk_src(p, tl, blockIdx.x);
       if (first) bulk_load(smp, first, kSpanSamples * 2, bar_smp);
+      if (const int16_t* second = tile_bulk_src(p, tl, blockIdx.x + gridDim.x)) bulk_prefetch_l2(second, kSpanSamples * 2);
       int it = 0;
       bool ok = true;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
@@ -340,7 +343,12 @@ __global__ void __launch_bounds__(kThreads, 1) k1_dft16(K1Params p, const uint4*
         KT_DECL;
         // the next tile's samples start towards L2 now; its bulk copy follows when this tile's rows are done
         const int16_t* nxt = tile_bulk_src(p, tl, tile + gridDim.x);
-        if (nxt) bulk_prefetch_l2(nxt, kSpanSamples * 2);
+        const int16_t* nxt2 = tile_bulk_src(p, tl, tile + 2 * gridDim.x);
+        if (nxt2) bulk_prefetch_l2(nxt2, kSpanSamples * 2);
+        // the row threads take their samples into registers first thing: the next tile's bulk copy can
+        // start as soon as they have, and lands under this tile's arithmetic
+        if (ok) ok = mbar_wait(bar_smp_free, (unsigned)it & 1u);
+        if (nxt && ok) bulk_load(smp, nxt, kSpanSamples * 2, bar_smp);
         if (ok && it >= 2) ok = mbar_wait(bar_acc_free + b, (unsigned)((it >> 1) - 1) & 1u);
         KT_MARK(5, true);
         const unsigned acc = tmem + (unsigned)(b * kN);
@@ -360,8 +368,6 @@ __global__ void __launch_bounds__(kThreads, 1) k1_dft16(K1Params p, const uint4*
         }
         umma_commit(bar_acc_full + b);
         KT_MARK(6, true);
-        // every row thread is done with the samples (all eight steps were ready): the next tile's can arrive
-        if (nxt && ok) bulk_load(smp, nxt, kSpanSamples * 2, bar_smp);
 #ifdef K1_TIMING
         if (blockIdx.x == 0) atomicAdd(&g_k1_cycles[15], 1ULL);
 #endif
@@ -408,26 +414,52 @@ __global__ void __launch_bounds__(kThreads, 1) k1_dft16(K1Params p, const uint4*
         asm volatile("bar.sync 1, %0;" ::"n"(kRowThreads) : "memory");
       }
       KT_MARK(2, ptid == 32);
-      // ---- rows: unit = (chunk of eight t, window slot); consecutive threads take consecutive slots
+      // ---- rows: unit = (chunk of eight t, window slot); consecutive threads take consecutive slots.
+      // First the raw samples of all of a thread's units (at most kMaxUnits) into registers, so that the
+      // sample buffer is free for the next tile's bulk copy while the arithmetic runs.
+      constexpr int kMaxUnits = (15 * 64 + kRowThreads - 1) / kRowThreads;
+      uint4 raw_u[kMaxUnits], raw_l[kMaxUnits];
+      float raw_pu[kMaxUnits], raw_pl[kMaxUnits];
+#pragma unroll
+      for (int i = 0; i < kMaxUnits; i++) {
+        const int u = ptid + i * kRowThreads;
+        raw_u[i] = make_uint4(0u, 0u, 0u, 0u);
+        raw_l[i] = raw_u[i];
+        raw_pu[i] = 0.0f;
+        raw_pl[i] = 0.0f;
+        if (u < 15 * 64) {
+          const int c = u >> 6, w = u & 63;
+          const Slot sl = tile_slots[w];
+          if (sl.flags & 2) {
+            const short* x = smp + (sl.flags >> 16) * run_stride + ((sl.flags >> 8) & 0xff) * kS;
+            const int nu = 120 + 8 * c, nl = 112 - 8 * c;  // first sample of the upper / lower eight
+            raw_u[i] = *reinterpret_cast<const uint4*>(x + nu);
+            raw_l[i] = *reinterpret_cast<const uint4*>(x + nl);
+            raw_pu[i] = (float)x[nu - 1];
+            // the state entering sample 0 is the last sample of the previous window, i.e. sample
+            // P - 1 of this one (speedy.c:416-425); 0 before the first window
+            raw_pl[i] = nl > 0 ? (float)x[nl - 1] : (sl.k >= 1 ? (float)x[kP - 1] : 0.0f);
+          }
+        }
+      }
+      mbar_arrive(bar_smp_free);
       bool ok = true;
-#pragma unroll 1
-      for (int u = ptid; u < 15 * 64; u += kRowThreads) {
+#pragma unroll
+      for (int i = 0; i < kMaxUnits; i++) {
+        const int u = ptid + i * kRowThreads;
+        if (u >= 15 * 64) break;
         const int c = u >> 6, w = u & 63;
         const Slot sl = tile_slots[w];
         uint4 s_hi = make_uint4(0u, 0u, 0u, 0u), s_lo = s_hi, d_hi = s_hi, d_lo = s_hi;
         if (sl.flags & 2) {
-          const short* x = smp + (sl.flags >> 16) * run_stride + ((sl.flags >> 8) & 0xff) * kS;
-          const int k = sl.k;
-          const int nu = 120 + 8 * c, nl = 112 - 8 * c;  // first sample of the upper / lower eight
-          const uint4 qu = *reinterpret_cast<const uint4*>(x + nu);
-          const uint4 ql = *reinterpret_cast<const uint4*>(x + nl);
+          const int nu = 120 + 8 * c, nl = 112 - 8 * c;
+          const uint4 qu = raw_u[i];
+          const uint4 ql = raw_l[i];
           const float4 hu0 = *reinterpret_cast<const float4*>(s_win + nu), hu1 = *reinterpret_cast<const float4*>(s_win + nu + 4);
           const float4 hl0 = *reinterpret_cast<const float4*>(s_win + nl), hl1 = *reinterpret_cast<const float4*>(s_win + nl + 4);
           float xu[9], xl[9];  // [0] = the sample before
-          xu[0] = (float)x[nu - 1];
-          // the state entering sample 0 is the last sample of the previous window, i.e. sample
-          // P - 1 of this one (speedy.c:416-425); 0 before the first window
-          xl[0] = nl > 0 ? (float)x[nl - 1] : (k >= 1 ? (float)x[kP - 1] : 0.0f);
+          xu[0] = raw_pu[i];
+          xl[0] = raw_pl[i];
           const unsigned wu[4] = {qu.x, qu.y, qu.z, qu.w}, wlw[4] = {ql.x, ql.y, ql.z, ql.w};
 #pragma unroll
           for (int i = 0; i < 4; i++) {
