@@ -113,6 +113,7 @@ __global__ void __launch_bounds__(kWarps * 32) k2_tension(K2Params p, float alph
     // ---- energy low-pass, sequential (speedy.c:517-518) ----------------------
     float my_lp = 0.0f;
     const int n_have = min(32, kB - kA - j0);
+#pragma unroll 8
     for (int i = 0; i < n_have; i++) {
       const float e_i = __shfl_sync(0xffffffffu, ef.x, i);
       lp_e = __fadd_rn(__fmul_rn(one_minus_alpha, e_i), __fmul_rn(alpha, lp_e));
@@ -161,6 +162,7 @@ __global__ void __launch_bounds__(kWarps * 32) k2_tension(K2Params p, float alph
 
     // ---- difference low-pass, sequential (speedy.c:698-699, 722-724) -----------
     float my_lpd = 0.0f;
+#pragma unroll 8
     for (int i = 0; i < n_have; i++) {
       const float x_i = __shfl_sync(0xffffffffu, ewld, i);
       const int live_i = __shfl_sync(0xffffffffu, (int)live, i);
@@ -184,16 +186,33 @@ __global__ void __launch_bounds__(kWarps * 32) k2_tension(K2Params p, float alph
       v0 = (float)fmax(0.01, fmin(1.0, (double)__fsub_rn(Rg, slope)));
     }
     // ---- duration feedback, sequential (speedy.c:778-785) ----------------------
+    //   requested += fmax(0.01, strength * excess)   (double)      excess = current - desired duration
+    //   current += frame / requested;  desired += frame / R_g
+    // Only `excess` carries from frame to frame.  Everything that does not depend on it is worked out by
+    // the 32 lanes beforehand, off the chain: fmax picks the constant 0.01 unless strength * excess exceeds
+    // it (a float exceeds the double 0.01 iff it exceeds the largest float below it, 0x3C23D70A), and then
+    // the frame's speed w = (float)((double)v0 + 0.01) and its duration frame / w are known in advance;
+    // otherwise the double sum of the two floats is exact, so its rounding is the float sum's.  The chain
+    // keeps a subtract, a multiply, a compare and an add per frame (and a division in the rare branch).
+    const float fb_floor = __uint_as_float(0x3C23D70Au);
+    const float w0 = fb > 0.0f ? (float)((double)v0 + 0.01) : v0;
+    const float q0 = __fdiv_rn(frame_duration, w0);
     float v = v0;
+#pragma unroll 8
     for (int i = 0; i < n_have; i++) {
       const int live_i = __shfl_sync(0xffffffffu, (int)live, i);
-      float v_i = __shfl_sync(0xffffffffu, v0, i);
+      float v_i = __shfl_sync(0xffffffffu, w0, i);
+      float q_i = __shfl_sync(0xffffffffu, q0, i);
+      const float v0_i = __shfl_sync(0xffffffffu, v0, i);
       if (live_i) {
         if (fb > 0.0f) {
-          const float excess = __fsub_rn(cur_dur, des_dur);
-          v_i = (float)((double)v_i + fmax(0.01, (double)__fmul_rn(fb, excess)));
+          const float fbx = __fmul_rn(fb, __fsub_rn(cur_dur, des_dur));
+          if (fbx > fb_floor) {
+            v_i = __fadd_rn(v0_i, fbx);
+            q_i = __fdiv_rn(frame_duration, v_i);
+          }
         }
-        cur_dur = __fadd_rn(cur_dur, __fdiv_rn(frame_duration, v_i));
+        cur_dur = __fadd_rn(cur_dur, q_i);
         des_dur = __fadd_rn(des_dur, des_step);
         if (i == lane) v = v_i;
       }
