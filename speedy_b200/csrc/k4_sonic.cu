@@ -174,6 +174,13 @@ struct Sonic {
       for (int i = vl; i < total; i += VL) {
         if (i < room) o[i] = (short)w32[o0 + i];
       }
+    } else if (nch() == 2) {
+      // stereo: a frame is one aligned 32-bit word on both sides (room is a whole number of frames)
+      const int* p32 = reinterpret_cast<const int*>(buf) + o0;
+      int* o32 = reinterpret_cast<int*>(o);
+      for (int t = vl; t < n; t += VL) {
+        if (2 * t < room) o32[t] = p32[t];
+      }
     } else {
       const short* p = buf + (size_t)o0 * nch();
       for (int i = vl; i < total; i += VL) {
@@ -241,11 +248,25 @@ struct Sonic {
           if (t < room) o[t] = (short)(num < 0 ? -q : q);
         }
       }
+    } else if (nch() == 2) {
+      // stereo: one frame (two samples) per lane and pass, 32-bit loads and stores
+      const int* dp32 = reinterpret_cast<const int*>(buf) + d0;
+      const int* up32 = reinterpret_cast<const int*>(buf) + u0;
+      int* o32 = reinterpret_cast<int*>(o);
+      for (int t = vl; t < n; t += VL) {
+        const int dw = dp32[t], uw = up32[t];
+        const int num_l = (int)(short)(dw & 0xffff) * (n - t) + (int)(short)(uw & 0xffff) * t;
+        const int num_r = (dw >> 16) * (n - t) + (uw >> 16) * t;
+        const int ql = n == 1 ? abs(num_l) : (int)(__umulhi((unsigned)abs(num_l), magic) >> shift);
+        const int qr = n == 1 ? abs(num_r) : (int)(__umulhi((unsigned)abs(num_r), magic) >> shift);
+        const int l = num_l < 0 ? -ql : ql, r = num_r < 0 ? -qr : qr;
+        if (2 * t < room) o32[t] = (l & 0xffff) | (r << 16);
+      }
     } else {
       const short* dp = buf + (size_t)d0 * nch();
       const short* up_ = buf + (size_t)u0 * nch();
       for (int i = vl; i < total; i += VL) {
-        int t = i / nch();
+        const int t = nch() == 2 ? (i >> 1) : i / nch();  // (stereo: no division per sample)
         const int num = (int)dp[i] * (n - t) + (int)up_[i] * t;
         const int q = n == 1 ? abs(num) : (int)(__umulhi((unsigned)abs(num), magic) >> shift);
         if (i < room) o[i] = (short)(num < 0 ? -q : q);
