@@ -109,6 +109,15 @@ def measured_peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def k1_error(sb):
+    """The tensor-core spectrogram kernel bounds every barrier wait and records a time-out in an
+    error word instead of hanging the device; a line with a non-zero word is not a valid measurement."""
+    import ctypes as C
+    f = sb.lib().speedyDebugK1Dft16Error
+    f.restype = C.c_int
+    return int(f())
+
+
 def host_link_ceiling(world, in_bytes, out_bytes):
     """The measured concurrent host<->device copy ceiling of this pool's boxes for `world` GPUs
     copying at once (profiles/r02_pcie_ceiling.jsonl, made by profiles/tools/pcie_ceiling.py under
@@ -455,6 +464,7 @@ def run_cuda_arm(args):
                     "host_link_ceiling": ceiling,
                     "frac_of_host_link_ceiling": (ceiling["both_directions_ms"] / e2e_ms) if ceiling else None},
             "gpu_launches": int(launches),
+            "k1_dft16_barrier_timeouts": k1_error(sb),
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
             "clocks": clocks,

@@ -536,6 +536,11 @@ speedyBatch speedyBatchCreate(const speedyBatchConfig* cfg) {
   for (int i = 0; i < kPipeEvents; i++) b->ev_pipe[i] = nullptr;
   b->d_tap_spec = b->d_tap_energy = b->d_tap_features = b->d_tap_tension = b->d_tap_speed = nullptr;
   make_geometry(cfg->sample_rate, cfg->num_channels, cfg->match_matlab, &b->g);
+  if (k1_uses_dft16(b->g) && cfg->analysis_frame_step <= 0 && k1_dft16_prepare() != cudaSuccess) {
+    set_error("speedyBatchCreate: the DFT matrix of the tensor-core spectrogram kernel could not be uploaded");
+    delete b;
+    return nullptr;
+  }
   if (cfg->analysis_frame_step > 0) {  // white-box hook: explicit analysis frames (speedy_b200.h)
     b->g.step = cfg->analysis_frame_step;
     b->g.partial = b->g.window - (b->g.window / b->g.step) * b->g.step;

@@ -657,6 +657,13 @@ static const uint4* dft_matrix(cudaError_t* err) {
   return table[dev];
 }
 
+// The matrix is built and uploaded when a batch is created (a synchronous allocation and copy have no
+// place on a launch path that may be under stream capture).
+cudaError_t k1_dft16_prepare() {
+  cudaError_t e = cudaSuccess;
+  return dft_matrix(&e) ? cudaSuccess : e;
+}
+
 cudaError_t launch_k1_dft16(const K1Params& p, cudaStream_t stream) {
   cudaError_t e = cudaSuccess;
   const uint4* dft = dft_matrix(&e);

@@ -85,6 +85,7 @@ cudaError_t launch_k1(const K1Params& p, cudaStream_t stream);
 // the 16 kHz tensor-core shape (k1_dft16.cu): the transform as a tcgen05 GEMM, one persistent CTA per SM
 bool k1_dft16_supported(const K1Params& p);
 bool k1_uses_dft16(const Geometry& g);
+cudaError_t k1_dft16_prepare();  // per device, once: the DFT matrix
 cudaError_t launch_k1_dft16(const K1Params& p, cudaStream_t stream);
 
 // ---- K2/K3: recurrences, hysteresis, tension, speed ------------------------
