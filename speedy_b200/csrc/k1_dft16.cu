@@ -74,7 +74,6 @@ constexpr int kRows = 128, kK = 128, kN = 256;
 constexpr int kEpiWarps = 8, kRowWarps = 11;  // + one warp for the MMA issuer
 constexpr int kThreads = (kEpiWarps + kRowWarps + 1) * 32, kRowThreads = kRowWarps * 32;
 constexpr float kPreHi = 0.97f;                          // speedy.c:422
-constexpr float kPreLo = (float)(0.97 - (double)0.97f);  // remainder of the double constant
 
 // shared memory (bytes)
 constexpr int kOffBhi = 0, kOffBlo = 65536, kOffAhi = 131072, kOffAlo = 163840;
@@ -473,10 +472,11 @@ __global__ void __launch_bounds__(kThreads, 1) k1_dft16(K1Params p, const uint4*
           float vu[8], vl[8];
 #pragma unroll
           for (int i = 0; i < 8; i++) {
-            // y = x - 0.97 * previous (speedy.c:422, evaluated there in double): 0.97 as a float and
-            // its remainder, so the constant carries no error
-            vu[i] = __fmul_rn(__fmaf_rn(-kPreLo, xu[i], __fmaf_rn(-kPreHi, xu[i], xu[i + 1])), hu[i]);
-            vl[i] = __fmul_rn(__fmaf_rn(-kPreLo, xl[i], __fmaf_rn(-kPreHi, xl[i], xl[i + 1])), hl[i]);
+            // y = x - 0.97 * previous (speedy.c:422, evaluated there in double).  One fused multiply-add
+            // with the float constant: its 2e-8 relative error is far below the 2^-21 of the fp16 split
+            // that follows (the FFT kernels, which keep fp32 throughout, carry the constant's remainder too)
+            vu[i] = __fmul_rn(__fmaf_rn(-kPreHi, xu[i], xu[i + 1]), hu[i]);
+            vl[i] = __fmul_rn(__fmaf_rn(-kPreHi, xl[i], xl[i + 1]), hl[i]);
           }
           // t = 8c + i pairs sample 120 + t (vu[i]) with sample 119 - t (vl[7 - i])
           float sv[8], dv[8];
