@@ -90,3 +90,31 @@ def test_product_does_not_link_the_oracle():
         for line in open(os.path.join(ROOT, "speedy_b200", f)):
             if "import" in line or "CDLL" in line:
                 assert "oracle" not in line, (f, line)
+
+
+def test_ctypes_mirrors_match_the_header_structs(tmp_path):
+    """The Python mirrors of the C structs (tests and bench.py go through them) have the header's
+    sizes and field offsets: compiled with gcc from include/speedy_b200.h, no GPU involved."""
+    import subprocess
+    src = tmp_path / "sizes.c"
+    src.write_text(r'''
+#include <stddef.h>
+#include <stdio.h>
+#include "speedy_b200.h"
+int main(void) {
+  printf("%zu %zu %zu %zu\n", sizeof(speedyBatchConfig), offsetof(speedyBatchConfig, max_write_frames),
+         offsetof(speedyBatchConfig, threads_per_stream), offsetof(speedyBatchConfig, analysis_frame_step));
+  printf("%zu %zu %zu\n", sizeof(speedySessionPoolConfig), offsetof(speedySessionPoolConfig, min_speed),
+         offsetof(speedySessionPoolConfig, auto_step_sessions));
+  printf("%zu %zu %zu\n", sizeof(speedySessionPoolStats), offsetof(speedySessionPoolStats, open_sessions),
+         offsetof(speedySessionPoolStats, last_step_ms));
+  return 0;
+}
+''')
+    exe = tmp_path / "sizes"
+    subprocess.run(["gcc", "-I" + os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    rows = [[int(x) for x in line.split()] for line in subprocess.run([str(exe)], capture_output=True, text=True).stdout.splitlines()]
+    B, P, S = sb.BatchConfig, sb.SessionPoolConfig, sb.SessionPoolStats
+    assert rows[0] == [C.sizeof(B), B.max_write_frames.offset, B.threads_per_stream.offset, B.analysis_frame_step.offset]
+    assert rows[1] == [C.sizeof(P), P.min_speed.offset, P.auto_step_sessions.offset]
+    assert rows[2] == [C.sizeof(S), S.open_sessions.offset, S.last_step_ms.offset]
