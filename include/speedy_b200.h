@@ -49,8 +49,12 @@ int sonicWriteFloatToStream(sonicStream stream, const float* inBuffer,
                             int sampleCount);
 int sonicReadFloatFromStream(sonicStream stream, float* outBuffer,
                              int bufferSize);
-/* sonic2.h:70, soniclib.c:169-175.  Stored; playback-rate conversion is not on
- * the hot path and any value other than 1.0 is rejected at the next write. */
+/* sonic2.h:70, soniclib.c:169-175 (forwards to upstream Sonic's sonicSetRate).  The
+ * frames the speed change produced are resampled by upstream Sonic's classic
+ * linear-interpolation rate change (output frames = input / (speed * rate), pitch
+ * scaled by rate), on the host between the device output and the read FIFO; rate 1
+ * costs nothing.  Parity unpinned: upstream Sonic is not part of the reference tree
+ * and no reference test sets a rate. */
 void sonicSetRate(sonicStream stream, float rate);
 /* sonic2.h:71, soniclib.c:177-183.  Global speed R_g. */
 void sonicSetSpeed(sonicStream stream, float speed);
@@ -115,7 +119,7 @@ int sonicIntFlushStream(sonicStream stream);
  * (chunking never changes the output, tests/test_gpu_parity.py); only WHEN output becomes
  * readable differs from the reference.  All drop-in calls of section 1 work on pooled
  * handles except the five debug callbacks (a pooled handle ignores them: taps of thousands
- * of sessions are what the batched API's taps are for) and sonicSetRate != 1.
+ * of sessions are what the batched API's taps are for).
  * sonicDestroyStream closes the session and frees its slot.  Calls are serialised by a
  * mutex per pool.  Setting the environment variable SPEEDY_B200_POOL_SESSIONS=<n> makes
  * plain sonicCreateStream open its handles from an implicit pool of n sessions per

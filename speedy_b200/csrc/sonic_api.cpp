@@ -42,6 +42,11 @@ struct sonicStreamStruct {
   bool flushed;      // nothing pending since the last sonicFlushStream
   long long out_capacity;
   std::vector<short> fifo;     // produced, not yet read (interleaved)
+  // sonicSetRate: upstream Sonic resamples what the speed change produced (adjustRate)
+  std::vector<short> rate_pitch;  // speed-changed frames not yet resampled (upstream's pitch buffer)
+  int old_rate_pos, new_rate_pos;
+  size_t flush_mark;              // FIFO length when the current flush began (rate != 1 only)
+  size_t last_drain_frames;       // frames the last drain took from the device
   std::vector<short> scratch;  // one batch read
   // callbacks (sonic2.h:100-124)
   tensionFunction on_tension;
@@ -79,11 +84,83 @@ static bool ensure_batch(sonicStream s) {
   return s->batch != nullptr;
 }
 
+// ---- playback rate (sonicSetRate, sonic2.h:70, soniclib.c:169-175 -> upstream sonicSetRate) ----
+// Upstream Sonic changes the playback rate after the speed change, by resampling its output: the
+// classic implementation's adjustRate / interpolate (linear interpolation between neighbouring
+// frames, integer positions old * newRate against new * oldRate with both rates halved until they
+// fit 14 bits), restated here on the host because the drop-in API hands frames out through a host
+// FIFO anyway.  It is outside the hot path (no BASELINE configuration sets a rate) and, like the
+// rest of upstream Sonic, unpinned: the reference clones upstream at HEAD, whose later revisions
+// resample with a windowed sinc instead.
+static void rate_resample(sonicStream s) {
+  const int C = s->channels;
+  int new_rate = (int)((float)s->sample_rate / s->rate), old_rate = s->sample_rate;
+  while (new_rate > (1 << 14) || old_rate > (1 << 14)) {
+    new_rate >>= 1;
+    old_rate >>= 1;
+  }
+  if (new_rate < 1) new_rate = 1;
+  if (old_rate < 1) old_rate = 1;
+  const size_t n = s->rate_pitch.size() / C;
+  size_t position = 0;
+  for (; position + 1 < n; position++) {  // (one frame stays behind: the right neighbour of the next output)
+    while ((long long)(s->old_rate_pos + 1) * new_rate > (long long)s->new_rate_pos * old_rate) {
+      const short* in = s->rate_pitch.data() + position * C;
+      for (int c = 0; c < C; c++) {
+        const int left = in[c], right = in[c + C];
+        const int pos = s->new_rate_pos * old_rate;
+        const int left_pos = s->old_rate_pos * new_rate, right_pos = (s->old_rate_pos + 1) * new_rate;
+        const int ratio = right_pos - pos, width = right_pos - left_pos;
+        s->fifo.push_back((short)((ratio * left + (width - ratio) * right) / width));
+      }
+      s->new_rate_pos++;
+    }
+    s->old_rate_pos++;
+    if (s->old_rate_pos == old_rate) {
+      s->old_rate_pos = 0;
+      s->new_rate_pos = 0;
+    }
+  }
+  s->rate_pitch.erase(s->rate_pitch.begin(), s->rate_pitch.begin() + position * C);
+}
+
+// frames the device produced for this handle -> the FIFO sonicRead* pops from
+static void append_output(sonicStream s, const short* src, size_t frames) {
+  if (s->rate == 1.0f && s->rate_pitch.empty()) {
+    s->fifo.insert(s->fifo.end(), src, src + frames * s->channels);
+    return;
+  }
+  s->rate_pitch.insert(s->rate_pitch.end(), src, src + frames * s->channels);
+  if (s->rate == 1.0f) {  // the rate went back to 1: what was waiting for a right neighbour goes out as it is
+    s->fifo.insert(s->fifo.end(), s->rate_pitch.begin(), s->rate_pitch.end());
+    s->rate_pitch.clear();
+    return;
+  }
+  rate_resample(s);
+}
+
+// sonicFlushStream with a rate: upstream expects (remaining / speed + pitch frames) / rate + 0.5 more
+// frames, resamples the silence it pads with as well, trims to that count and empties the pitch buffer
+static void begin_rate_flush(sonicStream s) { s->flush_mark = s->fifo.size(); }
+static void finish_rate_flush(sonicStream s, size_t pitch_before, size_t flushed_frames) {
+  if (s->rate == 1.0f) return;
+  const int C = s->channels;
+  const size_t expected = (size_t)((float)(flushed_frames + pitch_before) / s->rate + 0.5f);
+  const short zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int guard = 0; (s->fifo.size() - s->flush_mark) / C < expected && guard < (1 << 20); guard++) {
+    for (int c = 0; c < C; c += 8) s->rate_pitch.insert(s->rate_pitch.end(), zero, zero + (C - c < 8 ? C - c : 8));
+    rate_resample(s);
+  }
+  if ((s->fifo.size() - s->flush_mark) / C > expected) s->fifo.resize(s->flush_mark + expected * C);
+  s->rate_pitch.clear();
+}
+
 static bool drain_device_output(sonicStream s) {
   int32_t count = 0;
   s->scratch.resize((size_t)s->out_capacity * s->channels);
   if (!speedyBatchRead(s->batch, s->scratch.data(), s->out_capacity, &count)) return false;
-  s->fifo.insert(s->fifo.end(), s->scratch.begin(), s->scratch.begin() + (size_t)count * s->channels);
+  s->last_drain_frames = (size_t)count;
+  append_output(s, s->scratch.data(), (size_t)count);
   return true;
 }
 
@@ -169,7 +246,8 @@ bool pool_collect(speedySessionPool p) {
     sonicStream h = p->slots[i];
     if (h) {
       const short* src = p->h_out + (size_t)i * p->out_cap * p->channels;
-      h->fifo.insert(h->fifo.end(), src, src + (size_t)c * p->channels);
+      h->last_drain_frames = (size_t)c;
+      append_output(h, src, (size_t)c);
     }
     if (c >= p->out_cap) full = true;
   }
@@ -215,7 +293,6 @@ bool pool_reset_slot(speedySessionPool p, int slot) {
 int pool_write(sonicStream s, const short* in, int count) {
   speedySessionPool p = s->pool;
   std::lock_guard<std::mutex> lock(p->mu);
-  if (s->rate != 1.0f) return 0;  // playback-rate conversion is not on this path
   s->started = true;
   // (the same rule as a private handle: a flushed session that switches between the linear
   // short circuit and Speedy starts Speedy's clock at zero, soniclib.c:397-399)
@@ -250,7 +327,12 @@ int pool_flush(sonicStream s) {
   p->mask[s->slot] = 1;
   if (!speedyBatchFlushStreams(p->batch, p->mask.data())) return 0;
   s->flushed = true;
-  return pool_collect(p) ? 1 : 0;
+  const size_t pitch_before = s->rate_pitch.size() / s->channels;
+  begin_rate_flush(s);
+  s->last_drain_frames = 0;
+  if (!pool_collect(p)) return 0;
+  finish_rate_flush(s, pitch_before, s->last_drain_frames);
+  return 1;
 }
 
 void pool_set_param(sonicStream s, std::vector<float> speedySessionPoolStruct::*field, float value) {
@@ -303,7 +385,6 @@ sonicStream implicit_pool_open(int rate, int channels) {
 static int write_frames(sonicStream s, const short* in, int count) {
   if (!s) return 0;
   if (s->pool) return pool_write(s, in, count);
-  if (s->rate != 1.0f) return 0;  // playback-rate conversion is not on this path
   if (!ensure_batch(s)) return 0;
   s->started = true;
   // A flushed handle that switches between the linear short circuit and Speedy starts
@@ -354,6 +435,10 @@ static sonicStream new_handle(int sampleRate, int numChannels) {
   s->channels = numChannels;
   s->speed = 1.0f;      // soniclib.c:114
   s->rate = 1.0f;
+  s->old_rate_pos = 0;
+  s->new_rate_pos = 0;
+  s->flush_mark = 0;
+  s->last_drain_frames = 0;
   s->nonlinear = 0.0f;  // soniclib.c:117
   s->feedback = 0.1f;   // soniclib.c:122
   s->batch = nullptr;
@@ -536,7 +621,15 @@ int sonicReadFloatFromStream(sonicStream s, float* outBuffer, int bufferSize) {
 }
 
 void sonicSetRate(sonicStream s, float rate) {
-  if (s) s->rate = rate;
+  if (!s || !(rate > 0.0f)) return;
+  std::unique_lock<std::mutex> lock;
+  if (s->pool) {  // queued samples are processed (and resampled) at the rate they were written with
+    lock = std::unique_lock<std::mutex>(s->pool->mu);
+    pool_step_if_pending(s);
+  }
+  s->rate = rate;
+  s->old_rate_pos = 0;  // upstream sonicSetRate
+  s->new_rate_pos = 0;
 }
 
 void sonicSetSpeed(sonicStream s, float speed) {
@@ -551,7 +644,11 @@ int sonicFlushStream(sonicStream s) {
   if (!s || !ensure_batch(s)) return 0;
   if (!speedyBatchFlush(s->batch)) return 0;
   s->flushed = true;
-  return drain_device_output(s) ? 1 : 0;
+  const size_t pitch_before = s->rate_pitch.size() / s->channels;
+  begin_rate_flush(s);
+  if (!drain_device_output(s)) return 0;
+  finish_rate_flush(s, pitch_before, s->last_drain_frames);
+  return 1;
 }
 
 void sonicEnableNonlinearSpeedup(sonicStream s, float nonlinearFactor) {
