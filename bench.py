@@ -83,6 +83,22 @@ select_config(2)
 NCU_SUMMARY = "r02_kernels.json" if os.path.exists(os.path.join(ROOT, "profiles", "r02_kernels.json")) else "r01_kernels.json"
 
 
+def ncu_issue(ms_per_step, sm_mhz):
+    """The issue roofline of the step: warp instructions of one step (the committed ncu capture:
+    one launch of each kernel covers the step) against one instruction per scheduler per cycle
+    (148 SMs x 4 schedulers x the SM clock sampled during the timed region)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", NCU_SUMMARY)) as f:
+            ks = json.load(f)["kernels"]
+        inst = int(sum(k["warp_instructions"] for k in ks))
+        mhz = float(sm_mhz) if sm_mhz else 1965.0
+        ceiling_ms = inst / (148 * 4 * mhz * 1e6) * 1e3
+        return {"warp_instructions_per_step": inst, "ceiling_ms": ceiling_ms, "frac": ceiling_ms / ms_per_step,
+                "sm_mhz": mhz, "source": "profiles/%s" % NCU_SUMMARY}
+    except Exception:
+        return None
+
+
 def ncu_traffic(kernel_substr):
     """dram read + write bytes of one launch of the named kernel over the whole batch,
     from the committed ncu --set full capture (profiles/r01_kernels.json, taken with
@@ -436,6 +452,9 @@ def run_cuda_arm(args):
                            "achieved": (in_bytes + out_bytes) / (ms_per_step / 1e3) / 1e9,
                            "frac": (in_bytes + out_bytes) / (ms_per_step / 1e3) / 1e9 / peak},
         }
+        if CFG["number"] == 2 and n == 1024 and SECONDS == 60:
+            # the path is bound by instruction issue and dependent latency, not by bytes
+            roofline["issue"] = ncu_issue(ms_per_step, (clocks or {}).get("sm_mhz"))
         cpu_baseline = None
         if world == 1 and not args.no_cpu_baseline:
             ol, kind = load_reference()

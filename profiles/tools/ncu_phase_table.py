@@ -23,21 +23,21 @@ data = [r for r in rows[hi+1:] if len(r) > ix['# Samples'] and r[ix['# Samples']
 def phase(loc):
     if loc is None: return 'none'
     f, ln = loc
-    if f == 'amdf16.cuh':
-        if ln <= 120: return 'amdf blocks (sad/loads)'
-        if ln <= 155: return 'amdf resolve/udiv'
-        if ln <= 193: return 'amdf search setup+part store'
-        if ln <= 245: return 'amdf pick'
-        if ln <= 296: return 'amdf decimate'
+    if f == 'amdf16.cuh':  # (line ranges of the tree this table was last made from: see the commit)
+        if ln <= 122: return 'amdf blocks (sad/loads)'
+        if ln <= 156: return 'amdf resolve/udiv'
+        if ln <= 194: return 'amdf search setup+part store'
+        if ln <= 246: return 'amdf pick'
+        if ln <= 297: return 'amdf decimate'
         return 'amdf find_pitch glue'
     if f == 'k4_sonic.cu':
-        if 124 <= ln <= 137: return 'ensure'
-        if 139 <= ln <= 147: return 'advance_out'
-        if 150 <= ln <= 168: return 'emit_copy'
-        if 170 <= ln <= 215: return 'overlap_add'
-        if 553 <= ln <= 620: return 'process()'
-        if 639 <= ln <= 790: return 'kernel setup'
-        if 791 <= ln <= 871: return 'event loop'
+        if 124 <= ln <= 138: return 'ensure'
+        if 140 <= ln <= 148: return 'advance_out'
+        if 151 <= ln <= 194: return 'emit_copy'
+        if 195 <= ln <= 280: return 'overlap_add'
+        if 577 <= ln <= 682: return 'process()'
+        if 699 <= ln <= 849: return 'kernel setup'
+        if 850 <= ln <= 1008: return 'event loop'
         return 'k4 other %d' % (ln // 50 * 50)
     if f == 'common.cuh': return 'stage (refill)'
     return f

@@ -270,12 +270,19 @@ __device__ __forceinline__ void decimate(const Ctx& k, int off, Hook& hook) {
     hook.finish();
     int lo[4], hi[4];
     const int4 xs[4] = {x0, x1, x2, x3};
+    // (r is the same for the whole warp: one branch instead of a chain of selects per vector)
+    if (r == 0) {
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-      const int s01 = xs[q].x + xs[q].y;
-      const int l = r == 0 ? 0 : r == 1 ? xs[q].x : r == 2 ? s01 : s01 + xs[q].z;
-      lo[q] = l;
-      hi[q] = (s01 + (xs[q].z + xs[q].w)) - l;
+      for (int q = 0; q < 4; q++) { lo[q] = 0; hi[q] = (xs[q].x + xs[q].y) + (xs[q].z + xs[q].w); }
+    } else if (r == 1) {
+#pragma unroll
+      for (int q = 0; q < 4; q++) { lo[q] = xs[q].x; hi[q] = xs[q].y + xs[q].z + xs[q].w; }
+    } else if (r == 2) {
+#pragma unroll
+      for (int q = 0; q < 4; q++) { lo[q] = xs[q].x + xs[q].y; hi[q] = xs[q].z + xs[q].w; }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; q++) { lo[q] = xs[q].x + xs[q].y + xs[q].z; hi[q] = xs[q].w; }
     }
     const int nb = (k.lane + 1) & 31;
     int t[4];
