@@ -155,8 +155,9 @@ __global__ void __launch_bounds__(256) read_copy_warp_kernel(const int16_t* out,
 __global__ void __launch_bounds__(256) scatter_out_kernel(const int16_t* out, long long cap, int channels,
                                                           const int* upto, const int* done, int16_t* dst,
                                                           long long dst_stride, int n) {
-  // A small grid (the copy is PCIe-bound; it must not crowd the compute kernels out
-  // of the SMs): block b walks streams b, b + gridDim.x, ...
+  // A small grid (the copy is PCIe-bound; it must not crowd the compute kernels out of the SMs,
+  // nor the host-to-device copies out of the link: see the launch): block b walks streams b,
+  // b + gridDim.x, ...
   for (int s = blockIdx.x; s < n; s += gridDim.x) {
     long long a = done[s], b = upto[s];
     if (b > dst_stride) b = dst_stride;
@@ -1275,7 +1276,15 @@ int speedyBatchProcess(speedyBatch b, const int16_t* h_in, int64_t frames, int16
     if (h_out_dev) {
       // device-side scatter on the copy-out stream, ordered after chunk c's kernels
       if (cudaStreamWaitEvent(b->s_d2h, ev_done[c], 0) != cudaSuccess) return 0;
-      const int blocks = n < 48 ? n : 48;
+      // Eight blocks: enough to fill the link's device-to-host direction (a block sustains about
+      // 6.6 GB/s), few enough that the stores do not arrive in bursts that starve the read requests
+      // of the host-to-device copies running beside them (1024 x 60 s end to end: 2 / 4 / 8 / 16 /
+      // 48 / 148 blocks = 73.2 / 42.3 / 40.0 / 40.8 / 43.6 / 44.3 ms, profiles/README.md)
+      static const int scatter_blocks = [] {
+        const char* e = getenv("SPEEDY_B200_SCATTER_BLOCKS");
+        return e && atoi(e) > 0 ? atoi(e) : 8;
+      }();
+      const int blocks = n < scatter_blocks ? n : scatter_blocks;
       scatter_out_kernel<<<blocks, 256, 0, b->s_d2h>>>(b->d_out, b->out_capacity, C, b->d_snap[c % 3], b->d_done,
                                                        h_out_dev, out_stride_frames, n);
       scatter_advance_kernel<<<(n + 127) / 128, 128, 0, b->s_d2h>>>(n, b->d_snap[c % 3], b->d_done,
