@@ -1185,7 +1185,11 @@ int speedyBatchProcess(speedyBatch b, const int16_t* h_in, int64_t frames, int16
   // Chunk boundaries.  The kernels outrun PCIe, so what the call adds to the transfer
   // time is the work left when the last byte lands: the last chunks taper off
   // (..., 1, 1, 0.8, 0.6, 0.4, 0.2 of the regular size) to keep that tail short.
-  long long chunk = (frames + 9) / 10;
+  long long n_regular = 10;
+  if (const char* e = getenv("SPEEDY_B200_CHUNKS")) {
+    if (atoi(e) > 0) n_regular = atoi(e);
+  }
+  long long chunk = (frames + n_regular - 1) / n_regular;
   bool taper = true;
   if (const char* e = getenv("SPEEDY_B200_CHUNK_FRAMES")) {
     if (atoll(e) > 0) {
